@@ -1,0 +1,172 @@
+// bk_common.cuh -- context, operator descriptor and small device helpers shared by the
+// libbk200 translation units.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/bk200.h"
+
+#define BK_MAX_PAR 8
+#define BK_NSM_FALLBACK 148
+
+// Operator descriptor, passed BY VALUE to kernels.  Describes  out = a0*in + a1*J(u)*in  for the
+// named PDE stencils, optionally bordered (MatrixFreeBLSmap, src/LinearBorderSolver.jl:299-335).
+struct OpDesc {
+  int kind;
+  int nx, ny, nz;        // grid (potrap: nz = M time slices)
+  double cx, cy, cz;     // 1/h^2
+  double par[BK_MAX_PAR];
+  const double* u;       // linearisation state (device)
+  double a0, a1;         // a0 I + a1 J
+  long long N;           // unknowns of the un-bordered problem
+  // bordered map:  out.u = Op(x.u) + x.p * ba (+ bshift * x.u);  out.p = bscale*<bb, x.u> + bc * x.p
+  int bordered;
+  const double* ba;
+  const double* bb;
+  double bc, bshift, bscale;
+  // potrap extras
+  const double* phi;     // section (length N-1)
+  const double* fcache;  // F(x_i) cache, M slices (device)
+};
+
+struct Precond {
+  int kind = BK_PC_NONE;
+  double a0 = 0, a1 = 0;
+  // DCT/DST tables (device)
+  double2* tw[3] = {nullptr, nullptr, nullptr};     // FFT twiddles exp(-2 pi i k/n), k < n/2
+  double2* dtw[3] = {nullptr, nullptr, nullptr};    // DCT twiddles exp(-i pi k/(2n)), k < n
+  double* lam[3] = {nullptr, nullptr, nullptr};     // 1-D eigenvalues of the Laplacian factors
+  double* dense[3] = {nullptr, nullptr, nullptr};   // dense transform matrices for non power-of-two sizes (n x n, forward)
+  int pow2[3] = {0, 0, 0};
+  double* work = nullptr;                           // scratch vector (N)
+  double* work2 = nullptr;
+  // chan tridiagonal LU factors
+  double* tri = nullptr;
+};
+
+struct bk_ctx {
+  int device = 0;
+  int nsm = BK_NSM_FALLBACK;
+  cudaStream_t stream = nullptr;
+  int kind = 0;
+  long long dims[3] = {1, 1, 1};
+  double lengths[3] = {1, 1, 1};
+  double par[BK_MAX_PAR] = {0};
+  long long N = 0;        // unknowns
+  int m = 0;              // Krylov dimension capacity (basis holds m+1 vectors of length N+1)
+  long long ld = 0;       // leading dimension of the basis (>= N+1, multiple of 32)
+  // Jacobian state
+  double* u_state = nullptr;
+  double jpar[BK_MAX_PAR] = {0};
+  bool have_state = false;
+  // potrap
+  double* phi = nullptr;
+  double* xpi = nullptr;
+  double* fcache = nullptr;
+  double phi_dot_xpi = 0;
+  // Krylov workspace
+  double* V = nullptr;        // (m+1) x ld, unnormalised basis vectors v'_i
+  double* w = nullptr;        // ld
+  double* z = nullptr;        // ld  (preconditioned vector)
+  double* r = nullptr;        // ld
+  double* scales = nullptr;   // m+2 : s_i = 1/||v'_i||
+  double* gcoef = nullptr;    // m+2 : g_i = h_i * s_i (device), also lincomb coefficients
+  double* hcols = nullptr;    // (m+1) x (m+4) device H columns
+  double* hcols2 = nullptr;   // second-pass (CGS2) corrections
+  double* h_pinned = nullptr; // pinned host mirror of hcols (+ hcols2 behind it)
+  double* partials = nullptr; // (m+4) x Gmax
+  int gmax = 0;
+  unsigned int* counters = nullptr; // last-block tickets
+  double* red_out = nullptr;  // small device buffer for scalar reductions (16 doubles)
+  double* red_pinned = nullptr;
+  double* coef_pinned = nullptr; // m+2
+  std::vector<cudaEvent_t> events;
+  // staging buffers for host-pointer arguments
+  std::vector<double*> stage;  // each ld doubles
+  double* host_pinned = nullptr; // pinned bounce buffer (ld doubles) for pageable host memory
+  // generic temporaries for BLS/eigs
+  std::vector<double*> tmp;
+  Precond pc;
+  bk_stats stats = {0, 0, 0, 0.0, 0, 0};
+  bool timing = false;
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tpairs;
+  std::string err;
+};
+
+// ---- error helpers ---------------------------------------------------------------------------
+int bk_fail(bk_ctx* c, int code, const char* what, const char* file, int line);
+#define BK_CUDA(c, expr)                                                             \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) return bk_fail((c), BK_ERR_CUDA, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define BK_CHECK(c, cond, msg)                                                       \
+  do {                                                                               \
+    if (!(cond)) return bk_fail((c), BK_ERR_ARG, (msg), __FILE__, __LINE__);         \
+  } while (0)
+#define BK_TRY(expr)                 \
+  do {                               \
+    int _s = (expr);                 \
+    if (_s < 0) return _s;           \
+  } while (0)
+
+// ---- host-side internal API (cross-TU) ----------------------------------------------------------
+bool bk_is_device_ptr(const void* p);
+// Returns a device pointer for argument p (n doubles): p itself when device memory, else stage slot `slot`
+// filled by H2D (when `in`).  For outputs call bk_stage_out afterwards.
+int bk_stage_in(bk_ctx* c, const double* p, long long n, int slot, bool copy_in, double** dev);
+int bk_stage_out(bk_ctx* c, double* p, long long n, const double* dev);
+
+OpDesc bk_make_op(bk_ctx* c, double a0, double a1);
+OpDesc bk_make_residual_op(bk_ctx* c);
+int bk_launch_residual(bk_ctx* c, const double* u_dev, double* out_dev);
+// out = a0*in*in_scale + a1*J*(in*in_scale) [+ bordered terms]; in_scale_ptr (device, may be NULL => 1)
+int bk_launch_apply(bk_ctx* c, const OpDesc& op, const double* in_dev, const double* in_scale_ptr, double* out_dev);
+int bk_potrap_refresh_cache(bk_ctx* c);
+
+int bk_precond_apply_dev(bk_ctx* c, const double* in_dev, double* out_dev, long long n);
+
+// vector kernels (device pointers)
+int bk_dev_axpby(bk_ctx* c, double* y, double a, const double* x, double b, long long n);
+int bk_dev_scale(bk_ctx* c, double* x, double a, long long n);
+int bk_dev_dot(bk_ctx* c, const double* x, const double* y, long long n, double* out_host);
+int bk_dev_norminf(bk_ctx* c, const double* x, long long n, double* out_host);
+int bk_dev_copy(bk_ctx* c, double* dst, const double* src, long long n);
+
+// GMRES on device pointers; n = op.N (+1 if bordered)
+int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs_dev, double* x_dev, const bk_gmres_opts* o,
+                 int* converged, int* iters, double* resnorm);
+// Arnoldi building blocks (used by the eigensolver)
+int bk_tmp(bk_ctx* c, int slot, double** out);  // lazily allocated ld-sized temporaries
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double bk_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double bk_warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Grid-wide "last block done" ticket.  Returns true in exactly one block (the last to arrive),
+// after all other blocks' prior global writes are visible.  Resets the counter for the next launch.
+__device__ __forceinline__ bool bk_last_block(unsigned int* counter, int* s_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    int last = (t == gridDim.x * gridDim.y * gridDim.z - 1);
+    if (last) *counter = 0u;
+    *s_flag = last;
+  }
+  __syncthreads();
+  bool last = (*s_flag != 0);
+  if (last) __threadfence();
+  return last;
+}
+#endif

@@ -1,0 +1,553 @@
+// bk_krylov.cu -- K3: the GMRES(m) Arnoldi step on device and the GMRES driver (S1/S2).
+//
+// Replaces IterativeSolvers.gmres as called by (l::GMRESIterativeSolvers)(J, rhs; a0, a1)
+// (src/LinearSolver.jl:186-206): left/right preconditioning, tolerance max(reltol*||Pl\r0||, abstol)
+// on the preconditioned residual, `iters` = total inner iterations capped by maxiter, x updated at
+// restart and at the end.  Orthogonalisation is single-pass classical Gram-Schmidt in two sweeps
+// over the basis (the reference's backend uses modified GS => tolerance parity, not bit parity):
+//
+//   pass 1  k_fused_jvp_dots : w = a0 v_j + a1 J(u) v_j evaluated as the PDE stencil from a shared-memory
+//                              tile (bk_stencil.cuh) and, in the same kernel, h_i = <v_i, w> for i <= j
+//                              (warp-shuffle reduction -> per-CTA partials -> deterministic last-block sum).
+//                              Algorithmic traffic 8N(j+2) bytes: read u, V_1..V_j, write w.
+//   pass 2  k_update_norm    : v'_{j+1} = w - sum_i h_i v_i, ||v'_{j+1}||^2 reduced the same way.
+//                              Algorithmic traffic 8N(j+2): read w, V_1..V_j, write v'_{j+1}.
+//
+// The basis is stored UN-normalised (v'_i) with the scalars s_i = 1/||v'_i|| kept on device, so
+// normalisation costs no memory pass ("deferred as a scalar") and the host never has to be in the
+// loop to launch the next step: Givens rotations run on the host one iteration behind the GPU.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "bk_common.cuh"
+#include "bk_stencil.cuh"
+
+#define BK_DOT_UNROLL 4
+
+// ---- shared device code: dots of the thread-owned points against V_0..V_{j-1} + grid reduction ------
+// val/off: the EPT points this thread owns (off < 0 never occurs here: callers pass clamped offsets and
+// val = 0 for padding).  sred: shared scratch of >= 8*j doubles.
+__device__ __forceinline__ void bk_dots_reduce(const double (&val)[BK_EPT], const int (&off)[BK_EPT],
+                                               const double* __restrict__ V, long long ld, int j,
+                                               const double* __restrict__ scales, double* sred,
+                                               double* __restrict__ partials, unsigned int* counter,
+                                               double* __restrict__ hcol, double* __restrict__ gcoef, int* s_flag) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < j; i0 += BK_DOT_UNROLL) {
+    double acc[BK_DOT_UNROLL];
+    double ld_v[BK_DOT_UNROLL][BK_EPT];
+    const int nv = (j - i0) < BK_DOT_UNROLL ? (j - i0) : BK_DOT_UNROLL;
+#pragma unroll
+    for (int u = 0; u < BK_DOT_UNROLL; ++u) {
+      const double* Vi = V + (long long)(i0 + (u < nv ? u : 0)) * ld;
+#pragma unroll
+      for (int e = 0; e < BK_EPT; ++e) ld_v[u][e] = __ldg(Vi + off[e]);
+    }
+#pragma unroll
+    for (int u = 0; u < BK_DOT_UNROLL; ++u) {
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < BK_EPT; ++e) a = fma(ld_v[u][e], val[e], a);
+      acc[u] = bk_warp_sum(a);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < BK_DOT_UNROLL; ++u)
+        if (u < nv) sred[(i0 + u) * 8 + wid] = acc[u];
+    }
+  }
+  __syncthreads();
+  const int G = gridDim.x;
+  for (int i = threadIdx.x; i < j; i += blockDim.x) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[i * 8 + k];
+    partials[(long long)i * G + blockIdx.x] = t;
+  }
+  if (bk_last_block(counter, s_flag)) {
+    for (int i = wid; i < j; i += 8) {
+      double t = 0.0;
+      for (int k = lane; k < G; k += 32) t += __ldcg(partials + (long long)i * G + k);
+      t = bk_warp_sum(t);
+      if (lane == 0) {
+        double s = scales[i];
+        double h = s * t;
+        hcol[i] = h;
+        gcoef[i] = h * s;
+      }
+    }
+  }
+}
+
+// ---- pass 1, fused with the SH stencil ---------------------------------------------------------------
+template <int DIM>
+static __global__ void __launch_bounds__(BK_THREADS) k_fused_jvp_dots(OpDesc op, const double* __restrict__ in,
+                                                                      const double* __restrict__ in_scale_ptr,
+                                                                      double* __restrict__ w,
+                                                                      const double* __restrict__ V, long long ld, int j,
+                                                                      const double* __restrict__ scales,
+                                                                      double* __restrict__ partials,
+                                                                      unsigned int* counter, double* __restrict__ hcol,
+                                                                      double* __restrict__ gcoef) {
+  extern __shared__ double smem[];
+  __shared__ int s_flag;
+  double val[BK_EPT];
+  long long off64[BK_EPT];
+  int off[BK_EPT];
+  const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
+  sh_tile_eval<DIM, 0>(op, in, s, smem, val, off64);
+#pragma unroll
+  for (int e = 0; e < BK_EPT; ++e) {
+    if (off64[e] >= 0) w[off64[e]] = val[e];
+    off[e] = off64[e] >= 0 ? (int)off64[e] : 0;
+  }
+  __syncthreads();  // stencil tiles are dead: the same shared memory becomes the reduction scratch
+  bk_dots_reduce(val, off, V, ld, j, scales, smem, partials, counter, hcol, gcoef, &s_flag);
+}
+
+// ---- pass 1 without the stencil: w already in memory (left-preconditioned / non-fused operators) ---------
+static __global__ void __launch_bounds__(BK_THREADS) k_dots(const double* __restrict__ w, long long n,
+                                                            const double* __restrict__ V, long long ld, int j,
+                                                            const double* __restrict__ scales,
+                                                            double* __restrict__ partials, unsigned int* counter,
+                                                            double* __restrict__ hcol, double* __restrict__ gcoef) {
+  extern __shared__ double smem[];
+  __shared__ int s_flag;
+  double val[BK_EPT];
+  int off[BK_EPT];
+  const long long base = (long long)blockIdx.x * BK_TILE;
+#pragma unroll
+  for (int e = 0; e < BK_EPT; ++e) {
+    long long g = base + threadIdx.x + e * BK_THREADS;
+    bool ok = g < n;
+    off[e] = ok ? (int)g : 0;
+    val[e] = ok ? w[g] : 0.0;
+  }
+  bk_dots_reduce(val, off, V, ld, j, scales, smem, partials, counter, hcol, gcoef, &s_flag);
+}
+
+// ---- pass 2: v' = w - sum_i g_i V_i ; ||v'||^2 ---------------------------------------------------------
+static __global__ void __launch_bounds__(BK_THREADS) k_update_norm(const double* w, long long n,  // w may alias vout
+                                                                   const double* __restrict__ V, long long ld, int j,
+                                                                   const double* __restrict__ gcoef,
+                                                                   double* vout,
+                                                                   double* __restrict__ partials, unsigned int* counter,
+                                                                   double* __restrict__ h_out,
+                                                                   double* __restrict__ scale_out) {
+  __shared__ double s_w[8];
+  __shared__ int s_flag;
+  double val[BK_EPT];
+  int off[BK_EPT];
+  bool ok[BK_EPT];
+  const long long base = (long long)blockIdx.x * BK_TILE;
+#pragma unroll
+  for (int e = 0; e < BK_EPT; ++e) {
+    long long g = base + threadIdx.x + e * BK_THREADS;
+    ok[e] = g < n;
+    off[e] = ok[e] ? (int)g : 0;
+    val[e] = ok[e] ? w[g] : 0.0;
+  }
+  for (int i0 = 0; i0 < j; i0 += BK_DOT_UNROLL) {
+    double ld_v[BK_DOT_UNROLL][BK_EPT];
+    double gc[BK_DOT_UNROLL];
+    const int nv = (j - i0) < BK_DOT_UNROLL ? (j - i0) : BK_DOT_UNROLL;
+#pragma unroll
+    for (int u = 0; u < BK_DOT_UNROLL; ++u) {
+      const int i = i0 + (u < nv ? u : 0);
+      const double* Vi = V + (long long)i * ld;
+      gc[u] = (u < nv) ? gcoef[i] : 0.0;
+#pragma unroll
+      for (int e = 0; e < BK_EPT; ++e) ld_v[u][e] = __ldg(Vi + off[e]);
+    }
+#pragma unroll
+    for (int u = 0; u < BK_DOT_UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < BK_EPT; ++e) val[e] = fma(-gc[u], ld_v[u][e], val[e]);
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int e = 0; e < BK_EPT; ++e) {
+    if (ok[e]) {
+      vout[off[e]] = val[e];
+      acc = fma(val[e], val[e], acc);
+    }
+  }
+  acc = bk_warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_w[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int k = 0; k < 8; ++k) t += s_w[k];
+    partials[blockIdx.x] = t;
+  }
+  if (bk_last_block(counter, &s_flag)) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) t += __ldcg(partials + k);
+    t = bk_warp_sum(t);
+    if (lane == 0) s_w[wid] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0;
+      for (int k = 0; k < 8; ++k) r += s_w[k];
+      double h = sqrt(r);
+      *h_out = h;
+      *scale_out = 1.0 / h;
+    }
+  }
+}
+
+// ---- x = beta x + sum_i coef_i * scales_i * V'_i -----------------------------------------------------------
+static __global__ void __launch_bounds__(BK_THREADS) k_lincomb(double* __restrict__ x, double beta, long long n,
+                                                               const double* __restrict__ V, long long ld, int k,
+                                                               const double* __restrict__ coef,
+                                                               const double* __restrict__ scales) {
+  const long long base = (long long)blockIdx.x * BK_TILE;
+  double val[BK_EPT];
+  int off[BK_EPT];
+  bool ok[BK_EPT];
+#pragma unroll
+  for (int e = 0; e < BK_EPT; ++e) {
+    long long g = base + threadIdx.x + e * BK_THREADS;
+    ok[e] = g < n;
+    off[e] = ok[e] ? (int)g : 0;
+    val[e] = (ok[e] && beta != 0.0) ? beta * x[g] : 0.0;
+  }
+  for (int i = 0; i < k; ++i) {
+    const double ci = coef[i] * (scales ? scales[i] : 1.0);
+    const double* Vi = V + (long long)i * ld;
+#pragma unroll
+    for (int e = 0; e < BK_EPT; ++e) val[e] = fma(ci, __ldg(Vi + off[e]), val[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < BK_EPT; ++e)
+    if (ok[e]) x[off[e]] = val[e];
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static inline int chunk_grid(long long n) { return (int)((n + BK_TILE - 1) / BK_TILE); }
+
+static bool fused_available(const OpDesc& op) { return (op.kind == BK_SH2D || op.kind == BK_SH3D) && !op.bordered; }
+
+static size_t dots_smem(int j) { return sizeof(double) * 8 * (size_t)(j > 0 ? j : 1); }
+
+static int launch_fused(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* w, int j, double* hcol) {
+  size_t red = dots_smem(j);
+  if (op.kind == BK_SH2D) {
+    size_t sm = ShSmem<2>::BYTES > red ? ShSmem<2>::BYTES : red;
+    static size_t cur = 0;
+    if (sm > cur) {
+      cudaFuncSetAttribute(k_fused_jvp_dots<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      cur = sm;
+    }
+    int g = sh_num_tiles<2>(op.nx, op.ny, 1);
+    k_fused_jvp_dots<2><<<g, BK_THREADS, sm, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
+                                                          c->counters + 0, hcol, c->gcoef);
+  } else {
+    size_t sm = ShSmem<3>::BYTES > red ? ShSmem<3>::BYTES : red;
+    static size_t cur = 0;
+    if (sm > cur) {
+      cudaFuncSetAttribute(k_fused_jvp_dots<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      cur = sm;
+    }
+    int g = sh_num_tiles<3>(op.nx, op.ny, op.nz);
+    k_fused_jvp_dots<3><<<g, BK_THREADS, sm, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
+                                                          c->counters + 0, hcol, c->gcoef);
+  }
+  c->stats.kernel_launches++;
+  BK_CUDA(c, cudaGetLastError());
+  return BK_OK;
+}
+
+static int launch_dots(bk_ctx* c, const double* w, long long n, int j, double* hcol) {
+  size_t sm = dots_smem(j);
+  static size_t cur = 48 * 1024;
+  if (sm > cur) {
+    cudaFuncSetAttribute(k_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cur = sm;
+  }
+  k_dots<<<chunk_grid(n), BK_THREADS, sm, c->stream>>>(w, n, c->V, c->ld, j, c->scales, c->partials, c->counters + 1, hcol,
+                                                       c->gcoef);
+  c->stats.kernel_launches++;
+  BK_CUDA(c, cudaGetLastError());
+  return BK_OK;
+}
+
+static int launch_update(bk_ctx* c, const double* w, long long n, int j, double* vout, double* h_out, double* scale_out) {
+  k_update_norm<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(w, n, c->V, c->ld, j, c->gcoef, vout, c->partials,
+                                                             c->counters + 2, h_out, scale_out);
+  c->stats.kernel_launches++;
+  BK_CUDA(c, cudaGetLastError());
+  return BK_OK;
+}
+
+static int launch_lincomb(bk_ctx* c, double* x, double beta, long long n, int k, const double* coef_dev, bool use_scales) {
+  k_lincomb<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(x, beta, n, c->V, c->ld, k, coef_dev,
+                                                         use_scales ? c->scales : nullptr);
+  c->stats.kernel_launches++;
+  BK_CUDA(c, cudaGetLastError());
+  return BK_OK;
+}
+
+struct TimerScope {
+  bk_ctx* c;
+  size_t idx;
+  bool on;
+  TimerScope(bk_ctx* c_) : c(c_), idx(0), on(c_->timing) {}
+  void begin(size_t i) {
+    if (!on) return;
+    idx = i;
+    while (c->tpairs.size() <= i) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      c->tpairs.push_back({a, b});
+    }
+    cudaEventRecord(c->tpairs[i].first, c->stream);
+  }
+  void end() {
+    if (on) cudaEventRecord(c->tpairs[idx].second, c->stream);
+  }
+};
+
+// One Arnoldi step k (0-based): basis v'_0..v'_k -> v'_{k+1}, H column k on device (+ async copy to pinned host).
+static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, long long n, int k, size_t* timer_slot) {
+  const int j = k + 1;
+  const int mh = c->m + 4;
+  double* hcol = c->hcols + (size_t)k * mh;
+  double* hcol2 = c->hcols2 + (size_t)k * mh;
+  const double* in = c->V + (size_t)k * c->ld;
+  const double* sp = c->scales + k;
+  const bool left = o->pc_side == BK_SIDE_LEFT && c->pc.kind != BK_PC_NONE;
+  const bool right = o->pc_side == BK_SIDE_RIGHT && c->pc.kind != BK_PC_NONE;
+  if (right) {
+    BK_TRY(bk_precond_apply_dev(c, in, c->z, n));
+    in = c->z;
+  }
+  const bool fuse = o->fused && fused_available(op) && !left;
+  TimerScope ts(c);
+  const double* wfin = c->w;
+  if (fuse) {
+    ts.begin((*timer_slot)++);
+    BK_TRY(launch_fused(c, op, in, sp, c->w, j, hcol));
+    ts.end();
+  } else {
+    BK_TRY(bk_launch_apply(c, op, in, sp, c->w));
+    if (left) {
+      BK_TRY(bk_precond_apply_dev(c, c->w, c->r, n));
+      wfin = c->r;
+    }
+    ts.begin((*timer_slot)++);
+    BK_TRY(launch_dots(c, wfin, n, j, hcol));
+    ts.end();
+  }
+  double* vnext = c->V + (size_t)(k + 1) * c->ld;
+  ts.begin((*timer_slot)++);
+  BK_TRY(launch_update(c, wfin, n, j, vnext, hcol + j, c->scales + k + 1));
+  ts.end();
+  if (o->orth == BK_ORTH_CGS2) {
+    BK_TRY(launch_dots(c, vnext, n, j, hcol2));
+    BK_TRY(launch_update(c, vnext, n, j, vnext, hcol + j, c->scales + k + 1));
+  }
+  size_t bytes = sizeof(double) * (size_t)(j + 1);
+  BK_CUDA(c, cudaMemcpyAsync(c->h_pinned + (size_t)k * mh, hcol, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (o->orth == BK_ORTH_CGS2)
+    BK_CUDA(c, cudaMemcpyAsync(c->h_pinned + (size_t)(c->m + 1) * mh + (size_t)k * mh, hcol2, sizeof(double) * j,
+                               cudaMemcpyDeviceToHost, c->stream));
+  BK_CUDA(c, cudaEventRecord(c->events[k], c->stream));
+  c->stats.last_fused_bytes += 8LL * n * (2LL * j + 4);
+  c->stats.last_fused_launches += 2;
+  return BK_OK;
+}
+
+// initial (preconditioned) residual -> v'_0, returns beta on the host
+static int init_residual(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, long long n, const double* rhs, const double* x,
+                         bool x_zero, double* beta) {
+  const bool left = o->pc_side == BK_SIDE_LEFT && c->pc.kind != BK_PC_NONE;
+  const double* r = rhs;
+  if (!x_zero) {
+    BK_TRY(bk_launch_apply(c, op, x, nullptr, c->w));
+    BK_TRY(bk_dev_axpby(c, c->w, 1.0, rhs, -1.0, n));  // w = rhs - A x
+    r = c->w;
+  }
+  if (left) {
+    BK_TRY(bk_precond_apply_dev(c, r, c->r, n));
+    r = c->r;
+  }
+  BK_TRY(launch_update(c, r, n, 0, c->V, c->red_out, c->scales));
+  BK_CUDA(c, cudaMemcpyAsync(c->red_pinned, c->red_out, 8, cudaMemcpyDeviceToHost, c->stream));
+  BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  *beta = c->red_pinned[0];
+  return BK_OK;
+}
+
+int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, const bk_gmres_opts* o, int* converged,
+                 int* iters, double* resnorm) {
+  const long long n = op.N + (op.bordered ? 1 : 0);
+  BK_CHECK(c, n + 1 <= c->ld + 1, "system larger than the context");
+  int restart = o->restart;
+  if (restart > c->m) restart = c->m;
+  if ((long long)restart > n) restart = (int)n;
+  BK_CHECK(c, restart >= 1, "restart must be >= 1");
+  const int maxiter = o->maxiter;
+  const int mh = c->m + 4;
+  const bool right = o->pc_side == BK_SIDE_RIGHT && c->pc.kind != BK_PC_NONE;
+  BK_CHECK(c, o->pc_side == BK_SIDE_NONE || c->pc.kind != BK_PC_NONE, "pc_side set but no preconditioner was set up");
+  c->stats.last_fused_bytes = 0;
+  c->stats.last_fused_launches = 0;
+  c->stats.last_fused_ms = 0.0;
+  size_t timer_slot = 0;
+
+  BK_CUDA(c, cudaMemsetAsync(x, 0, 8 * (size_t)n, c->stream));  // initially_zero = true (src/LinearSolver.jl:171)
+  bool x_zero = true;
+  int total = 0;
+  bool conv = false;
+  double tol = 0.0, res = 0.0;
+  std::vector<double> H((size_t)(restart + 1) * restart), g(restart + 1), cs(restart), sn(restart), y(restart);
+  bool first = true;
+  while (true) {
+    double beta = 0;
+    BK_TRY(init_residual(c, op, o, n, rhs, x, x_zero, &beta));
+    if (first) {
+      tol = fmax(o->reltol * beta, o->abstol);
+      first = false;
+    }
+    res = beta;
+    if (!(res > tol) || total >= maxiter || !(beta > 0.0)) {
+      conv = res <= tol;
+      break;
+    }
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int kl = 0, kd = 0;
+    bool stop = false;
+    while (true) {
+      bool can_launch = kl < restart && (total + (kl - kd)) < maxiter && !stop;
+      if (can_launch && (kl - kd) < 2) {
+        BK_TRY(arnoldi_step(c, op, o, n, kl, &timer_slot));
+        ++kl;
+        continue;
+      }
+      if (kd == kl) break;
+      BK_CUDA(c, cudaEventSynchronize(c->events[kd]));
+      // ---- Givens update of column kd on the host (one step behind the device) ----
+      const int k = kd;
+      const double* hc = c->h_pinned + (size_t)k * mh;
+      const double* hc2 = c->h_pinned + (size_t)(c->m + 1) * mh + (size_t)k * mh;
+      double* Hk = H.data() + (size_t)k * (restart + 1);
+      for (int i = 0; i <= k; ++i) Hk[i] = hc[i] + (o->orth == BK_ORTH_CGS2 ? hc2[i] : 0.0);
+      double hk1 = hc[k + 1];
+      for (int i = 0; i < k; ++i) {
+        double t = cs[i] * Hk[i] + sn[i] * Hk[i + 1];
+        Hk[i + 1] = -sn[i] * Hk[i] + cs[i] * Hk[i + 1];
+        Hk[i] = t;
+      }
+      double d = hypot(Hk[k], hk1);
+      if (!(d > 0.0) || !std::isfinite(d)) {
+        // unusable column (exact breakdown): stop with the columns gathered so far
+        stop = true;
+        break;
+      }
+      cs[k] = Hk[k] / d;
+      sn[k] = hk1 / d;
+      Hk[k] = d;
+      g[k + 1] = -sn[k] * g[k];
+      g[k] = cs[k] * g[k];
+      res = fabs(g[k + 1]);
+      ++kd;
+      ++total;
+      if (res <= tol || total >= maxiter || hk1 == 0.0) {
+        stop = true;
+        break;
+      }
+    }
+    const int k = kd;
+    if (k > 0) {
+      // back substitution R y = g
+      for (int i = k - 1; i >= 0; --i) {
+        double t = g[i];
+        for (int q = i + 1; q < k; ++q) t -= H[(size_t)q * (restart + 1) + i] * y[q];
+        y[i] = t / H[(size_t)i * (restart + 1) + i];
+      }
+      // in-flight speculative steps must not still be reading coef/gcoef: they only touch gcoef, not coef_pinned
+      for (int i = 0; i < k; ++i) c->coef_pinned[i] = y[i];
+      double* coef_dev = c->hcols2 + (size_t)c->m * mh;  // last row of hcols2 is free scratch
+      BK_CUDA(c, cudaMemcpyAsync(coef_dev, c->coef_pinned, 8 * (size_t)k, cudaMemcpyHostToDevice, c->stream));
+      if (right) {
+        BK_TRY(launch_lincomb(c, c->w, 0.0, n, k, coef_dev, true));
+        BK_TRY(bk_precond_apply_dev(c, c->w, c->z, n));
+        BK_TRY(bk_dev_axpby(c, x, 1.0, c->z, x_zero ? 0.0 : 1.0, n));
+      } else {
+        BK_TRY(launch_lincomb(c, x, x_zero ? 0.0 : 1.0, n, k, coef_dev, true));
+      }
+      BK_CUDA(c, cudaStreamSynchronize(c->stream));  // coef_pinned is reused by the next cycle
+      x_zero = false;
+    }
+    conv = res <= tol;
+    if (conv || total >= maxiter || k == 0) break;
+  }
+  BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->timing) {
+    double ms = 0;
+    for (size_t i = 0; i < timer_slot && i < c->tpairs.size(); ++i) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, c->tpairs[i].first, c->tpairs[i].second) == cudaSuccess) ms += t;
+    }
+    c->stats.last_fused_ms = ms;
+  }
+  if (converged) *converged = conv ? 1 : 0;
+  if (iters) *iters = total;
+  if (resnorm) *resnorm = res;
+  return conv ? BK_OK : BK_NOT_CONVERGED;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+static bk_gmres_opts default_opts() {
+  bk_gmres_opts o;
+  o.reltol = 1e-8;
+  o.abstol = 0.0;
+  o.restart = 200;
+  o.maxiter = 100;
+  o.pc_side = BK_SIDE_NONE;
+  o.orth = BK_ORTH_CGS;
+  o.fused = 1;
+  o.reserved = 0;
+  return o;
+}
+
+extern "C" int32_t bk_gmres(bk_ctx* c, const double* rhs, double* x, double a0, double a1, const bk_gmres_opts* opts,
+                            int32_t* converged, int32_t* iters, double* resnorm) {
+  if (!c) return BK_ERR_ARG;
+  BK_CHECK(c, c->have_state, "bk_jac_set_state must be called before bk_gmres");
+  bk_gmres_opts o = opts ? *opts : default_opts();
+  double *drhs, *dx;
+  BK_TRY(bk_stage_in(c, rhs, c->N, 4, true, &drhs));
+  BK_TRY(bk_stage_in(c, x, c->N, 5, false, &dx));
+  BK_CHECK(c, drhs != dx, "bk_gmres: rhs and x must not alias");
+  OpDesc op = bk_make_op(c, a0, a1);
+  int cv = 0, it = 0;
+  double rn = 0;
+  int st = bk_gmres_dev(c, op, drhs, dx, &o, &cv, &it, &rn);
+  if (st < 0) return st;
+  if (converged) *converged = cv;
+  if (iters) *iters = it;
+  if (resnorm) *resnorm = rn;
+  BK_TRY(bk_stage_out(c, x, c->N, dx));
+  return st;
+}
+
+extern "C" int32_t bk_gmres2(bk_ctx* c, const double* rhs1, const double* rhs2, double* x1, double* x2, double a0, double a1,
+                             const bk_gmres_opts* opts, int32_t* converged, int32_t iters[2]) {
+  // src/LinearSolver.jl:15-19: two sequential solves with the same operator, flag1 & flag2, (it1, it2)
+  int32_t c1 = 0, c2 = 0, i1 = 0, i2 = 0;
+  int s1 = bk_gmres(c, rhs1, x1, a0, a1, opts, &c1, &i1, nullptr);
+  if (s1 < 0) return s1;
+  int s2 = bk_gmres(c, rhs2, x2, a0, a1, opts, &c2, &i2, nullptr);
+  if (s2 < 0) return s2;
+  if (converged) *converged = c1 & c2;
+  if (iters) {
+    iters[0] = i1;
+    iters[1] = i2;
+  }
+  return (c1 & c2) ? BK_OK : BK_NOT_CONVERGED;
+}

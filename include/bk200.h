@@ -1,0 +1,146 @@
+/* bk200.h -- C ABI of libbk200.so: the B200-native Newton-Krylov corrector hot path of
+ * BifurcationKit.jl's pseudo-arclength continuation (PALC).
+ *
+ * Every entry point replaces the arithmetic behind one reference plugin surface; the citation
+ * after each prototype is the reference interface (file:line under the BifurcationKit.jl tree)
+ * whose work it performs.  The Julia-side binding (ccall stubs + the three plugin structs) is in
+ * julia/BK200.jl and INTEGRATION.md; the Python ctypes binding used by the tests and the
+ * benchmark is bifurcationkit.jl_b200/lib.py.
+ *
+ * Conventions
+ *   - Every function returns int32 status: 0 ok, >0 non-fatal (BK_NOT_CONVERGED), <0 error;
+ *     the message for the last error of a context is bk_last_error(ctx).  Nothing throws or
+ *     aborts across the boundary (the reference only logs linear-solver non-convergence,
+ *     src/LinearSolver.jl:202-205).
+ *   - All vectors are fp64.  A `const double*` / `double*` vector argument may be EITHER a host
+ *     pointer (option A: the library stages it through device scratch, H2D/D2H inside the call)
+ *     OR a device pointer obtained from bk_vec_alloc (option B: zero copies).  The library tells
+ *     them apart with cudaPointerGetAttributes.  The caller owns every pointer; the library never
+ *     retains a caller pointer past the call (bk_jac_set_state COPIES u).
+ *   - One context per GPU; a context is not thread-safe; calls are synchronous with respect to
+ *     host-visible outputs.
+ *   - Layout: Julia column-major, x fastest: u[i + j*Nx (+ k*Nx*Ny)], 0-based here.
+ */
+#ifndef BK200_H
+#define BK200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bk_ctx bk_ctx;
+
+enum { BK_OK = 0, BK_NOT_CONVERGED = 1, BK_ERR_ARG = -1, BK_ERR_CUDA = -2, BK_ERR_STATE = -3 };
+
+/* problem kinds = the named PDE stencils */
+enum {
+  BK_CHAN = 1,   /* examples/chan.jl:5-19,85-95      params (alpha, beta)            dims (n)        */
+  BK_SH2D = 2,   /* examples/SH2d-fronts.jl:13-34,124-127  params (l, nu)           dims (Nx,Ny)    */
+  BK_SH3D = 3,   /* examples/SH3d.jl:16-53           params (l, nu)                  dims (Nx,Ny,Nz) */
+  BK_CGL2D = 4,  /* examples/cGL2d.jl:6-22,262-318   params (r, mu, nu, c3, c5)      dims (Nx,Ny), N = 2 Nx Ny */
+  BK_POTRAP_CGL2D = 5 /* src/periodicorbit/PeriodicOrbitTrapeze.jl:209-330 over BK_CGL2D; dims (Nx,Ny,M), N = 2 Nx Ny M + 1 */
+};
+
+/* preconditioner kinds (the reference's Pl/Pr contract: src/Preconditioner.jl:11-37; the
+ * examples use sparse factorisations: SH2d-fronts.jl:120-122 lu(L1+I), SH3d.jl:88, chan.jl:108-111) */
+enum {
+  BK_PC_NONE = 0,
+  BK_PC_SH_DCT = 1,     /* (L1 + shift I)^-1 by separable DCT-II (exact for the Neumann-closure operator) */
+  BK_PC_CHAN_TRIDIAG = 2, /* lu(P), P = tridiagonal Laplacian with identity boundary rows (chan.jl:108-109) */
+  BK_PC_CGL_DST = 3     /* per-component (a0 I + a1 Lap_dirichlet)^-1 by DST-I (stand-in for cGL2d.jl:209-213 ILU) */
+};
+enum { BK_SIDE_NONE = 0, BK_SIDE_LEFT = 1, BK_SIDE_RIGHT = 2 };
+enum { BK_ORTH_CGS = 0, BK_ORTH_CGS2 = 1 };
+
+/* GMRES options = fields of GMRESIterativeSolvers (src/LinearSolver.jl:149-182) */
+typedef struct bk_gmres_opts {
+  double reltol;   /* 1e-8 */
+  double abstol;   /* 0    */
+  int32_t restart; /* 200  */
+  int32_t maxiter; /* 100  */
+  int32_t pc_side; /* BK_SIDE_*: which of Pl / Pr holds the context's preconditioner */
+  int32_t orth;    /* BK_ORTH_CGS (single classical Gram-Schmidt pass) or BK_ORTH_CGS2 */
+  int32_t fused;   /* 1: JVP fused into the Arnoldi dot-product kernel where available; 0: separate kernels */
+  int32_t reserved;
+} bk_gmres_opts;
+
+/* per-call statistics (all optional outputs may be NULL) */
+typedef struct bk_stats {
+  int64_t kernel_launches; /* kernels launched by this context since creation */
+  int64_t h2d_bytes, d2h_bytes;
+  double  last_fused_ms;   /* device time of the fused JVP+Arnoldi kernels in the last bk_gmres call (0 unless timing enabled) */
+  int64_t last_fused_bytes;/* algorithmic bytes moved by them, 8N(2j+4) summed over the iterations run */
+  int64_t last_fused_launches;
+} bk_stats;
+
+/* ---- context --------------------------------------------------------------------------- */
+int32_t bk_ctx_create(int32_t device, int32_t problem_kind, const int64_t dims[3], const double lengths[3],
+                      int32_t krylov_m, bk_ctx** out);
+int32_t bk_ctx_destroy(bk_ctx* ctx);
+const char* bk_last_error(bk_ctx* ctx);
+int64_t bk_problem_size(bk_ctx* ctx);                       /* N = number of unknowns of F */
+int32_t bk_set_params(bk_ctx* ctx, const double* params, int32_t n);
+int32_t bk_get_stats(bk_ctx* ctx, bk_stats* out);
+int32_t bk_set_timing(bk_ctx* ctx, int32_t on);              /* CUDA-event timing of the fused kernels */
+int32_t bk_sync(bk_ctx* ctx);
+void*   bk_stream(bk_ctx* ctx);                              /* cudaStream_t the kernels are launched on */
+
+/* ---- S11 device vectors: BorderedArray / VectorInterface algebra (src/BorderedArrays.jl:30-35,53-70,79-217) */
+int32_t bk_vec_alloc(bk_ctx* ctx, int64_t n, double** out);
+int32_t bk_vec_free(bk_ctx* ctx, double* v);
+int32_t bk_vec_upload(bk_ctx* ctx, double* dst_dev, const double* src_host, int64_t n);
+int32_t bk_vec_download(bk_ctx* ctx, double* dst_host, const double* src_dev, int64_t n);
+int32_t bk_vec_copy(bk_ctx* ctx, double* dst, const double* src, int64_t n);          /* _copyto! */
+int32_t bk_vec_zero(bk_ctx* ctx, double* x, int64_t n);                                 /* zerovector! */
+int32_t bk_vec_scale(bk_ctx* ctx, double* x, double a, int64_t n);                      /* VI.scale! */
+int32_t bk_vec_axpby(bk_ctx* ctx, double* y, double a, const double* x, double b, int64_t n); /* VI.add!(y,x,a,b): y = a x + b y */
+int32_t bk_vec_dot(bk_ctx* ctx, const double* x, const double* y, int64_t n, double* out); /* VI.inner */
+int32_t bk_vec_norm2(bk_ctx* ctx, const double* x, int64_t n, double* out);
+int32_t bk_vec_norminf(bk_ctx* ctx, const double* x, int64_t n, double* out);           /* normC = norminf, src/LinearSolver.jl:4 */
+/* S8: arc_length_eq (src/continuation/Palc.jl:44-56): theta*<x - x0, tau>/N in one fused reduction; out = <x - x0, tau> */
+int32_t bk_vec_diffdot(bk_ctx* ctx, const double* x, const double* x0, const double* tau, int64_t n, double* out);
+
+/* ---- K1/K2: the named PDE stencils ------------------------------------------------------- */
+int32_t bk_residual(bk_ctx* ctx, const double* u, double* out);        /* F(u; params)  (prob.VF.F, src/Problems.jl:133) */
+int32_t bk_jac_set_state(bk_ctx* ctx, const double* u);                /* J = jacobian(prob,u,params): copies u + current params (src/Problems.jl:98-101) */
+int32_t bk_jvp(bk_ctx* ctx, const double* v, double* out, double a0, double a1); /* out = a0 v + a1 J v (_axpy_op, src/LinearSolver.jl:46-62) */
+
+/* ---- K6: preconditioner --------------------------------------------------------------------- */
+int32_t bk_precond_setup(bk_ctx* ctx, int32_t kind, double a0, double a1); /* SH_DCT: (L1 + a0 I)^-1; CGL_DST: (a0 I + a1 Lap)^-1 */
+int32_t bk_precond_apply(bk_ctx* ctx, const double* in, double* out);  /* ldiv!(out, P, in) (src/Preconditioner.jl:11-37) */
+
+/* ---- S1/S2: GMRES = (l::GMRESIterativeSolvers)(J, rhs; a0, a1) (src/LinearSolver.jl:186-206, 15-19) */
+int32_t bk_gmres(bk_ctx* ctx, const double* rhs, double* x, double a0, double a1, const bk_gmres_opts* opts,
+                 int32_t* converged, int32_t* iters, double* resnorm);
+int32_t bk_gmres2(bk_ctx* ctx, const double* rhs1, const double* rhs2, double* x1, double* x2, double a0, double a1,
+                  const bk_gmres_opts* opts, int32_t* converged, int32_t iters[2]);
+
+/* ---- S3/S4/S5: bordered linear solvers (src/LinearBorderSolver.jl:88-166, 299-335, 404-437)
+ *   [ shift I + J     dR    ] [dX]   [R]
+ *   [ xiu dzu'      xip dzp ] [dl] = [n],     dotp(x,y) = dotscale * <x,y>  (PALC: 1/N, Palc.jl:4)      */
+int32_t bk_bls_bordering(bk_ctx* ctx, const double* dR, const double* dzu, double dzp, const double* R, double n,
+                         double xiu, double xip, int32_t has_shift, double shift, double dotscale,
+                         const bk_gmres_opts* opts, int32_t check_precision, int32_t k, double tol,
+                         double* dX, double* dl, int32_t* converged, int32_t iters[2]);
+int32_t bk_bls_matrixfree(bk_ctx* ctx, const double* dR, const double* dzu, double dzp, const double* R, double n,
+                          double xiu, double xip, int32_t has_shift, double shift, double dotscale,
+                          const bk_gmres_opts* opts, double* dX, double* dl, int32_t* converged, int32_t* iters);
+/* the bordered map alone: out = MatrixFreeBLSmap(J,a,b,c,shift)(x), x and out of length N+1 (src/LinearBorderSolver.jl:312-325) */
+int32_t bk_bls_map(bk_ctx* ctx, const double* a, const double* b, double c, int32_t has_shift, double shift, double dotscale,
+                   const double* x, double* out);
+
+/* ---- S10: shift-invert Arnoldi (src/EigSolver.jl:246-266; inner solver = bk_gmres with a0=-sigma)
+ *   vals sorted by decreasing real part; vecs (N x nev, column-major, real Schur/Ritz vectors; complex pairs
+ *   as (re, im) consecutive columns) may be NULL. */
+int32_t bk_eigs_shift_invert(bk_ctx* ctx, double sigma, int32_t nev, int32_t krylovdim, double tol, int32_t maxrestart,
+                             const bk_gmres_opts* inner, const double* v0, double* vals_re, double* vals_im, double* vecs,
+                             int32_t* nconv, int32_t* nops);
+
+/* ---- P5: trapezoid periodic-orbit functional over the context's vector field
+ *   (BK_POTRAP_CGL2D contexts; x = [x_1..x_M; T], src/periodicorbit/PeriodicOrbitTrapeze.jl:249-330) */
+int32_t bk_potrap_set_section(bk_ctx* ctx, const double* phi, const double* xpi); /* length N-1 each */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

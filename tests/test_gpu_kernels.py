@@ -1,0 +1,207 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the NumPy oracle on the same seeded inputs.
+Tolerances: stencil kernels 1e-12 relative (fp64, different summation order only); solves 1e-8 relative
+(the class the reference's own tests use, test/linear_solvers/test_linear.jl:120-122)."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from oracle import problems, krylov, bls as obls, potrap as opotrap
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bk():
+    return g.load_package()
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+LX, LY = 8 * np.pi, 4 * np.pi / np.sqrt(3)
+
+
+@pytest.mark.parametrize("dims", [(64, 32), (151, 100), (7, 5), (130, 67), (256, 256)])
+def test_sh2d_residual_jvp(bk, dims):
+    Nx, Ny = dims
+    sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
+    rng = np.random.default_rng(1)
+    u = problems.sh2d_sol0(Nx, Ny, LX, LY) + 0.1 * rng.standard_normal(sh.N)
+    v = rng.standard_normal(sh.N)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=8, params=(-0.1, 1.3))
+    assert _rel(ctx.residual(u), sh.F(u)) < 1e-12
+    J = ctx.jacobian(u)
+    assert _rel(J(v), sh.dF(u, v)) < 1e-12
+    assert _rel(ctx.jvp(v, a0=0.1, a1=0.9), 0.1 * v + 0.9 * sh.dF(u, v)) < 1e-12
+    # device-resident path gives the same bits as the host-pointer path
+    ud, vd = ctx.to_device(u), ctx.to_device(v)
+    assert np.array_equal(ctx.residual(ud).numpy(), ctx.residual(u))
+    assert np.array_equal(ctx.jvp(vd).numpy(), ctx.jvp(v))
+    # parameter change is seen by the residual but J keeps its snapshot
+    ctx.set_params((-0.3, 1.1))
+    assert _rel(ctx.residual(u), sh.F(u, l=-0.3) + (1.1 - 1.3) * u**2) < 1e-12
+    assert _rel(J(v), sh.dF(u, v)) < 1e-12
+
+
+@pytest.mark.parametrize("dims", [(22, 22, 22), (33, 9, 17), (64, 32, 16)])
+def test_sh3d_residual_jvp(bk, dims):
+    L = (np.pi, np.pi, np.pi)
+    sh = problems.SwiftHohenberg(dims, L, l=0.1, nu=1.2)
+    rng = np.random.default_rng(2)
+    u = problems.sh3d_sol0(*dims, *L) + 0.05 * rng.standard_normal(sh.N)
+    v = rng.standard_normal(sh.N)
+    ctx = bk.Context(bk.BK_SH3D, dims, L, krylov_m=8, params=(0.1, 1.2))
+    assert _rel(ctx.residual(u), sh.F(u)) < 1e-12
+    assert _rel(ctx.jacobian(u)(v), sh.dF(u, v)) < 1e-12
+
+
+def test_chan_residual_jvp(bk):
+    for n in (101, 1000):
+        rng = np.random.default_rng(3)
+        x = problems.chan_sol0(n) + 0.01 * rng.standard_normal(n)
+        dx = rng.standard_normal(n)
+        ctx = bk.Context(bk.BK_CHAN, (n,), (1.0,), krylov_m=8, params=(3.3, 0.01))
+        assert _rel(ctx.residual(x), problems.chan_F(x, 3.3, 0.01)) < 1e-13
+        assert _rel(ctx.jacobian(x)(dx), problems.chan_dF(x, dx, 3.3, 0.01)) < 1e-13
+
+
+def test_cgl_residual_jvp(bk):
+    for dims in ((41, 21), (64, 48)):
+        gl = problems.GinzburgLandau2D(dims[0], dims[1], np.pi, np.pi / 2, r=1.2)
+        rng = np.random.default_rng(4)
+        u, du = 0.3 * rng.standard_normal(gl.N), rng.standard_normal(gl.N)
+        ctx = bk.Context(bk.BK_CGL2D, dims, (np.pi, np.pi / 2), krylov_m=8, params=(1.2, 0.1, 1.0, -1.0, 1.0))
+        assert _rel(ctx.residual(u), gl.F(u)) < 1e-12
+        assert _rel(ctx.jacobian(u)(du), gl.dF(u, du)) < 1e-12
+
+
+def test_potrap_residual_jvp(bk):
+    Nx, Ny, M = 24, 12, 7
+    gl = problems.GinzburgLandau2D(Nx, Ny, np.pi, np.pi / 2, r=1.3)
+    rng = np.random.default_rng(5)
+    NM = gl.N * M
+    x = np.concatenate([0.3 * rng.standard_normal(NM), [6.1]])
+    dx = np.concatenate([rng.standard_normal(NM), [0.7]])
+    phi, xpi = rng.standard_normal(NM), rng.standard_normal(NM)
+    tr = opotrap.Trapeze(gl.F, gl.dF, phi, xpi, M, gl.N)
+    ctx = bk.Context(bk.BK_POTRAP_CGL2D, (Nx, Ny, M), (np.pi, np.pi / 2), krylov_m=8, params=(1.3, 0.1, 1.0, -1.0, 1.0))
+    assert ctx.N == NM + 1
+    ctx.potrap_set_section(phi, xpi)
+    assert _rel(ctx.residual(x), tr.residual(x)) < 1e-12
+    assert _rel(ctx.jacobian(x)(dx), tr.jvp(x, dx)) < 1e-12
+
+
+def test_vector_algebra(bk):
+    ctx = bk.Context(bk.BK_CHAN, (100003,), (1.0,), krylov_m=4, params=(3.3, 0.01))
+    rng = np.random.default_rng(6)
+    a, b, c = (rng.standard_normal(ctx.N) for _ in range(3))
+    A, B, Cv = ctx.to_device(a), ctx.to_device(b), ctx.to_device(c)
+    assert abs(A.dot(B) - a @ b) < 1e-9 * np.linalg.norm(a) * np.linalg.norm(b)
+    assert abs(A.norm() - np.linalg.norm(a)) < 1e-12 * np.linalg.norm(a)
+    assert A.norminf() == np.max(np.abs(a))
+    assert abs(A.diffdot(B, Cv) - (a - b) @ c) < 1e-9 * np.linalg.norm(a - b) * np.linalg.norm(c)
+    Y = B.copy().axpby_(0.3, A, -1.7)
+    assert np.allclose(Y.numpy(), 0.3 * a - 1.7 * b, rtol=1e-15, atol=1e-15)
+    assert np.allclose(A.copy().scale_(2.5).numpy(), 2.5 * a)
+    assert np.all(A.copy().zero_().numpy() == 0)
+    # reductions are deterministic (last-block scheme, no atomics on data)
+    assert A.dot(B) == A.dot(B)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("orth", ["cgs", "cgs2"])
+def test_gmres_sh2d_vs_oracle(bk, fused, orth):
+    dims = (96, 64)
+    sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
+    u = problems.sh2d_sol0(*dims, LX, LY)
+    rng = np.random.default_rng(7)
+    rhs = rng.standard_normal(sh.N)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=80, params=(-0.1, 1.3))
+    J = ctx.jacobian(u)
+    ols = krylov.GMRESIterativeSolvers(reltol=1e-10, restart=80, maxiter=80)
+    ls = bk.GMRESB200(reltol=1e-10, restart=80, maxiter=80, orth=orth, fused=fused)
+    for a0, a1 in ((3.0, -1.0), (0.0, 1.0)):
+        xo, oko, ito = ols(lambda v: sh.dF(u, v), rhs, a0=a0, a1=a1)
+        x, ok, it = ls(J, rhs, a0=a0, a1=a1)
+        assert ok == oko
+        if oko:
+            assert abs(it - ito) <= 2, (it, ito)
+            assert _rel(x, xo) < 1e-8
+            # true residual
+            A = a0 * np.eye(1)[0, 0]
+            r = rhs - (a0 * x + a1 * sh.dF(u, x))
+            assert np.linalg.norm(r) <= 2e-10 * np.linalg.norm(rhs) * 5
+        # device-resident rhs
+        xd, okd, itd = ls(J, ctx.to_device(rhs), a0=a0, a1=a1)
+        assert itd == it and np.array_equal(xd.numpy(), x)
+
+
+def test_gmres_restart_and_maxiter(bk):
+    dims = (64, 32)
+    sh = problems.SwiftHohenberg(dims, (LX, LY))
+    u = problems.sh2d_sol0(*dims, LX, LY)
+    rhs = np.random.default_rng(8).standard_normal(sh.N)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=20, params=(-0.1, 1.3))
+    J = ctx.jacobian(u)
+    x, ok, it = bk.GMRESB200(reltol=1e-9, restart=10, maxiter=400)(J, rhs, a0=3.0, a1=-1.0)
+    xo, oko, ito = krylov.GMRESIterativeSolvers(reltol=1e-9, restart=10, maxiter=400)(lambda v: sh.dF(u, v), rhs, a0=3.0, a1=-1.0)
+    assert ok and oko and abs(it - ito) <= 3
+    assert _rel(x, xo) < 1e-7
+    x, ok, it = bk.GMRESB200(reltol=1e-14, restart=20, maxiter=5)(J, rhs, a0=3.0, a1=-1.0)
+    assert (not ok) and it == 5  # never throws on non-convergence (src/LinearSolver.jl:202-205)
+
+
+def test_gmres_sh3d_and_generic_ops(bk):
+    # SH3d (fused 3-D stencil), chan and cGL (generic operator path)
+    dims, L = (24, 20, 16), (np.pi, np.pi, np.pi)
+    sh = problems.SwiftHohenberg(dims, L, l=0.1, nu=1.2)
+    u = problems.sh3d_sol0(*dims, *L)
+    rhs = np.random.default_rng(9).standard_normal(sh.N)
+    ctx = bk.Context(bk.BK_SH3D, dims, L, krylov_m=100, params=(0.1, 1.2))
+    x, ok, it = bk.GMRESB200(reltol=1e-10, restart=100, maxiter=100)(ctx.jacobian(u), rhs, a0=40.0, a1=-1.0)
+    xo, oko, ito = krylov.GMRESIterativeSolvers(reltol=1e-10, restart=100, maxiter=100)(lambda v: sh.dF(u, v), rhs, a0=40.0, a1=-1.0)
+    assert ok and oko and abs(it - ito) <= 2 and _rel(x, xo) < 1e-8
+    gl = problems.GinzburgLandau2D(24, 12, np.pi, np.pi / 2, r=1.2)
+    ug = 0.3 * np.random.default_rng(10).standard_normal(gl.N)
+    rg = np.random.default_rng(11).standard_normal(gl.N)
+    ctx2 = bk.Context(bk.BK_CGL2D, (24, 12), (np.pi, np.pi / 2), krylov_m=200, params=(1.2, 0.1, 1.0, -1.0, 1.0))
+    x, ok, it = bk.GMRESB200(reltol=1e-10, restart=200, maxiter=200)(ctx2.jacobian(ug), rg, a0=60.0, a1=-1.0)
+    xo, oko, ito = krylov.GMRESIterativeSolvers(reltol=1e-10, restart=200, maxiter=200)(lambda v: gl.dF(ug, v), rg, a0=60.0, a1=-1.0)
+    assert ok and oko and abs(it - ito) <= 2 and _rel(x, xo) < 1e-8
+
+
+def test_bls_map_and_bordered_solvers(bk):
+    """test/linear_solvers/test_linear.jl:71-85,172-244 restated on the SH2d Jacobian."""
+    dims = (48, 32)
+    sh = problems.SwiftHohenberg(dims, (LX, LY))
+    u = problems.sh2d_sol0(*dims, LX, LY)
+    rng = np.random.default_rng(12)
+    N = sh.N
+    a, b, R = rng.standard_normal(N), rng.standard_normal(N), rng.standard_normal(N)
+    c, n = 0.37, -0.81
+    x = rng.standard_normal(N + 1)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=150, params=(-0.1, 1.3))
+    J = ctx.jacobian(u)
+    Jd = sh.jac_sparse(u).toarray()
+    for shift in (None, 2.5):
+        m = obls.MatrixFreeBLSmap(Jd, a, b, c, shift, lambda p, q: np.dot(p, q) / N)
+        assert _rel(bk.bls_map(J, a, b, c, x, shift=shift, dotscale=1.0 / N), m(x)) < 1e-12
+    # bordered solves on the shifted (well conditioned) operator  (shift I + J) with shift = -3
+    shift, xiu, xip, dzp = -3.0, 0.5, 0.5, 0.9
+    A = np.zeros((N + 1, N + 1))
+    A[:N, :N] = Jd + shift * np.eye(N)
+    A[:N, N] = a
+    A[N, :N] = xiu * b / N
+    A[N, N] = xip * dzp
+    ref = np.linalg.solve(A, np.concatenate([R, [n]]))
+    ls = bk.GMRESB200(reltol=1e-12, restart=150, maxiter=150)
+    for solver in (bk.BorderingBLSB200(ls, check_precision=False), bk.BorderingBLSB200(ls, check_precision=True, k=2),
+                   bk.MatrixFreeBLSB200(ls)):
+        dX, dl, ok, it = solver(J, a, b, dzp, R, n, xiu, xip, shift=shift, dotscale=1.0 / N)
+        assert ok, type(solver)
+        assert _rel(dX, ref[:N]) < 1e-8 and abs(dl - ref[N]) < 1e-8 * max(1, abs(ref[N])), type(solver)
+        # device-resident arguments
+        dXd, dld, okd, _ = solver(J, ctx.to_device(a), ctx.to_device(b), dzp, ctx.to_device(R), n, xiu, xip,
+                                  shift=shift, dotscale=1.0 / N)
+        assert _rel(dXd.numpy(), ref[:N]) < 1e-8 and abs(dld - ref[N]) < 1e-8 * max(1, abs(ref[N]))
