@@ -301,3 +301,19 @@ class ShiftInvertB200:
                                                _l.ptr(vecs) if want_vectors else None, C.byref(nconv), C.byref(nops)))
         vals = re + 1j * im
         return vals, (vecs.T if want_vectors else None), nconv.value >= nev, nops.value
+
+
+def hessenberg_eig(H, vectors=True):
+    """Host-only: eigenpairs of a real upper-Hessenberg matrix through the library's QR iteration."""
+    lib = _l.load()
+    H = np.asfortranarray(H, dtype=np.float64)
+    n = H.shape[0]
+    wr, wi = np.zeros(n), np.zeros(n)
+    vr = np.zeros((n, n), order="F")
+    vi = np.zeros((n, n), order="F")
+    dp = C.POINTER(C.c_double)
+    st = lib.bk_hessenberg_eig(H.ctypes.data_as(dp), n, n, wr.ctypes.data_as(dp), wi.ctypes.data_as(dp),
+                               vr.ctypes.data_as(dp) if vectors else None, vi.ctypes.data_as(dp) if vectors else None)
+    if st != 0:
+        raise _l.BK200Error(f"bk_hessenberg_eig failed ({st})")
+    return wr + 1j * wi, (vr + 1j * vi) if vectors else None

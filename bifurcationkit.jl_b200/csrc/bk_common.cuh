@@ -87,6 +87,11 @@ struct bk_ctx {
   double* host_pinned = nullptr; // pinned bounce buffer (ld doubles) for pageable host memory
   // generic temporaries for BLS/eigs
   std::vector<double*> tmp;
+  // eigensolver workspace (lazily allocated)
+  double* Q = nullptr;       // (qcap+1) x ld Arnoldi basis of the shift-invert operator
+  int qcap = 0;
+  double* eig_dev = nullptr; // ones (qcap+2) | hcolA (qcap+2) | hcolB (qcap+2) | g (qcap+2) | coef (2*(qcap+2))
+  double* eig_pinned = nullptr;
   Precond pc;
   bk_stats stats = {0, 0, 0, 0.0, 0, 0};
   bool timing = false;
@@ -138,7 +143,14 @@ int bk_dev_copy(bk_ctx* c, double* dst, const double* src, long long n);
 // GMRES on device pointers; n = op.N (+1 if bordered)
 int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs_dev, double* x_dev, const bk_gmres_opts* o,
                  int* converged, int* iters, double* resnorm);
-// Arnoldi building blocks (used by the eigensolver)
+// Arnoldi building blocks (used by the eigensolver): dots h_i = s_i <B_i, w> (also g_i = h_i s_i), update
+// vout = w - sum g_i B_i with its norm -> *h_out, 1/norm -> *scale_out, and x = beta x + sum coef_i s_i B_i.
+int bk_launch_dots(bk_ctx* c, const double* basis, const double* scales, const double* w, long long n, int j, double* hcol,
+                   double* gcoef);
+int bk_launch_update(bk_ctx* c, const double* basis, const double* gcoef, const double* w, long long n, int j, double* vout,
+                     double* h_out, double* scale_out);
+int bk_launch_lincomb(bk_ctx* c, const double* basis, const double* scales, double* x, double beta, long long n, int k,
+                      const double* coef_dev);
 int bk_tmp(bk_ctx* c, int slot, double** out);  // lazily allocated ld-sized temporaries
 
 // ---- device helpers ---------------------------------------------------------------------------

@@ -133,7 +133,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   double* bufs[] = {c->u_state, c->V, c->w, c->z, c->r, c->scales, c->gcoef, c->hcols, c->hcols2, c->partials,
-                    c->red_out, c->phi, c->xpi, c->fcache, c->pc.work, c->pc.work2, c->pc.tri};
+                    c->red_out, c->phi, c->xpi, c->fcache, c->pc.work, c->pc.work2, c->pc.tri, c->Q, c->eig_dev};
   for (double* b : bufs)
     if (b) cudaFree(b);
   for (int d = 0; d < 3; ++d) {
@@ -151,6 +151,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
   if (c->red_pinned) cudaFreeHost(c->red_pinned);
   if (c->coef_pinned) cudaFreeHost(c->coef_pinned);
   if (c->host_pinned) cudaFreeHost(c->host_pinned);
+  if (c->eig_pinned) cudaFreeHost(c->eig_pinned);
   for (auto& e : c->events)
     if (e) cudaEventDestroy(e);
   for (auto& p : c->tpairs) {

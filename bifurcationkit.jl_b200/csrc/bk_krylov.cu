@@ -259,34 +259,45 @@ static int launch_fused(bk_ctx* c, const OpDesc& op, const double* in, const dou
   return BK_OK;
 }
 
-static int launch_dots(bk_ctx* c, const double* w, long long n, int j, double* hcol) {
+int bk_launch_dots(bk_ctx* c, const double* basis, const double* scales, const double* w, long long n, int j, double* hcol,
+                   double* gcoef) {
   size_t sm = dots_smem(j);
   static size_t cur = 48 * 1024;
   if (sm > cur) {
     cudaFuncSetAttribute(k_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     cur = sm;
   }
-  k_dots<<<chunk_grid(n), BK_THREADS, sm, c->stream>>>(w, n, c->V, c->ld, j, c->scales, c->partials, c->counters + 1, hcol,
-                                                       c->gcoef);
+  k_dots<<<chunk_grid(n), BK_THREADS, sm, c->stream>>>(w, n, basis, c->ld, j, scales, c->partials, c->counters + 1, hcol,
+                                                       gcoef);
   c->stats.kernel_launches++;
   BK_CUDA(c, cudaGetLastError());
   return BK_OK;
 }
+static int launch_dots(bk_ctx* c, const double* w, long long n, int j, double* hcol) {
+  return bk_launch_dots(c, c->V, c->scales, w, n, j, hcol, c->gcoef);
+}
 
-static int launch_update(bk_ctx* c, const double* w, long long n, int j, double* vout, double* h_out, double* scale_out) {
-  k_update_norm<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(w, n, c->V, c->ld, j, c->gcoef, vout, c->partials,
+int bk_launch_update(bk_ctx* c, const double* basis, const double* gcoef, const double* w, long long n, int j, double* vout,
+                     double* h_out, double* scale_out) {
+  k_update_norm<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(w, n, basis, c->ld, j, gcoef, vout, c->partials,
                                                              c->counters + 2, h_out, scale_out);
   c->stats.kernel_launches++;
   BK_CUDA(c, cudaGetLastError());
   return BK_OK;
 }
+static int launch_update(bk_ctx* c, const double* w, long long n, int j, double* vout, double* h_out, double* scale_out) {
+  return bk_launch_update(c, c->V, c->gcoef, w, n, j, vout, h_out, scale_out);
+}
 
-static int launch_lincomb(bk_ctx* c, double* x, double beta, long long n, int k, const double* coef_dev, bool use_scales) {
-  k_lincomb<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(x, beta, n, c->V, c->ld, k, coef_dev,
-                                                         use_scales ? c->scales : nullptr);
+int bk_launch_lincomb(bk_ctx* c, const double* basis, const double* scales, double* x, double beta, long long n, int k,
+                      const double* coef_dev) {
+  k_lincomb<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(x, beta, n, basis, c->ld, k, coef_dev, scales);
   c->stats.kernel_launches++;
   BK_CUDA(c, cudaGetLastError());
   return BK_OK;
+}
+static int launch_lincomb(bk_ctx* c, double* x, double beta, long long n, int k, const double* coef_dev, bool use_scales) {
+  return bk_launch_lincomb(c, c->V, use_scales ? c->scales : nullptr, x, beta, n, k, coef_dev);
 }
 
 struct TimerScope {

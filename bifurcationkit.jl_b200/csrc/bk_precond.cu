@@ -1,14 +1,427 @@
-// bk_precond.cu -- K6 preconditioners (placeholder: filled in below)
+// bk_precond.cu -- K6: preconditioners honouring the reference's Pl/Pr contract
+// (ldiv!(y, P, x), src/Preconditioner.jl:11-37).
+//
+// BK_PC_SH_DCT: the examples precondition Swift-Hohenberg with a sparse factorisation of L1 + I
+//   (examples/SH2d-fronts.jl:120-122  Pl = lu(par.L1 + I); examples/SH3d.jl:88 cholesky(L1)).  The
+//   Neumann-closure Laplacian (SH2d-fronts.jl:13-29) is diagonalised by the DCT-II, so
+//   (L1 + shift I)^-1 r = IDCT( DCT(r) / ((1 + lx_i + ly_j [+ lz_k])^2 + shift) )  exactly
+//   (identity pinned in tests/test_oracle_palc.py::test_dct_symbol_diagonalises_L1).
+//   Each 1-D DCT of a power-of-two length is a shared-memory radix-2 complex FFT (Makhoul's
+//   reordering: v[m] = x[2m], v[n-1-m] = x[2m+1]; C[k] = Re(e^{-i pi k/2n} FFT(v)[k])); other lengths
+//   use a dense n x n transform.  Lines along x are contiguous; lines along y/z are processed in
+//   batches of W consecutive x so every global access stays coalesced.
+// BK_PC_CHAN_TRIDIAG: lu(P) of examples/chan.jl:108-111 (Thomas algorithm, one thread: n = 1e3 plumbing).
+// BK_PC_CGL_DST: per-component (a0 I + a1 Lap_dirichlet)^-1 by dense DST-I (stand-in for the ILU of
+//   examples/cGL2d.jl:209-213); for potrap contexts it is applied slice by slice (block Jacobi, cf.
+//   jacobian_block_diag, src/periodicorbit/PeriodicOrbitTrapeze.jl:619-643).
+#include <cmath>
+#include <utility>
+#include <vector>
 #include "bk_common.cuh"
+
+struct LineGeom {
+  int n;         // line length
+  long long es;  // element stride along the line
+  int nx;        // extent of the contiguous (batch) index; 1 for x-lines
+  long long os;  // stride of the outer index
+  int nouter;    // number of outer indices
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ int bitrev(int v, int logn) { return (int)(__brev((unsigned)v) >> (32 - logn)); }
+
+// In-place radix-2 DIT FFT on smem lines.  STRIDED: element e of line l at s[e*W + l]; else s[l*n + e].
+// inverse: conjugate twiddles (no 1/n scaling here).
+template <bool STRIDED>
+__device__ __forceinline__ void smem_fft(double2* s, int n, int logn, int W, const double2* __restrict__ tw, bool inverse) {
+  const int halfn = n >> 1;
+  for (int st = 0; st < logn; ++st) {
+    const int half = 1 << st;
+    const int tstep = halfn >> st;
+    for (int b = threadIdx.x; b < halfn * W; b += blockDim.x) {
+      int line, bf;
+      if (STRIDED) {
+        line = b % W;
+        bf = b / W;
+      } else {
+        line = b / halfn;
+        bf = b - line * halfn;
+      }
+      int grp = bf >> st, pos = bf & (half - 1);
+      int i0 = (grp << (st + 1)) + pos, i1 = i0 + half;
+      double2 t = __ldg(tw + pos * tstep);
+      if (inverse) t.y = -t.y;
+      double2* p0 = STRIDED ? s + (long long)i0 * W + line : s + (long long)line * n + i0;
+      double2* p1 = STRIDED ? s + (long long)i1 * W + line : s + (long long)line * n + i1;
+      double2 a = *p0, bb = cmul(t, *p1);
+      *p0 = make_double2(a.x + bb.x, a.y + bb.y);
+      *p1 = make_double2(a.x - bb.x, a.y - bb.y);
+    }
+    __syncthreads();
+  }
+}
+
+// DIR +1: forward DCT-II (unnormalised) of every line; DIR -1: its exact inverse.
+// SCALE (forward only used by the fused variant later): none here.
+template <bool STRIDED, int DIR>
+static __global__ void __launch_bounds__(256) k_dct_lines(const double* __restrict__ in, double* __restrict__ out, LineGeom g,
+                                                          int logn, int W, const double2* __restrict__ tw,
+                                                          const double2* __restrict__ dtw) {
+  extern __shared__ double2 sfft[];
+  const int n = g.n;
+  // which lines does this CTA own?
+  long long base;  // address of element 0 of line 0 of this CTA
+  int nl;          // number of valid lines
+  long long lstride;
+  if (STRIDED) {
+    int bx = blockIdx.x, o = blockIdx.y;
+    int x0 = bx * W;
+    nl = min(W, g.nx - x0);
+    base = x0 + (long long)o * g.os;
+    lstride = 1;
+  } else {
+    long long l0 = (long long)blockIdx.x * W;
+    nl = (int)min((long long)W, (long long)g.nouter - l0);
+    base = l0 * g.os;
+    lstride = g.os;
+  }
+  // load with Makhoul reordering + bit reversal
+  for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
+    int line, e;
+    if (STRIDED) {
+      line = q % W;
+      e = q / W;
+    } else {
+      line = q / n;
+      e = q - line * n;
+    }
+    double2 val = make_double2(0.0, 0.0);
+    int m;
+    if (DIR > 0) {
+      if (line < nl) val.x = in[base + line * lstride + (long long)e * g.es];
+      m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
+    } else {
+      // V[k] = conj(dtw[k]) * (C[k] - i C[n-k]),  C[n] = 0
+      if (line < nl) {
+        double ck = in[base + line * lstride + (long long)e * g.es];
+        double cnk = e > 0 ? in[base + line * lstride + (long long)(n - e) * g.es] : 0.0;
+        double2 t = __ldg(dtw + e);
+        t.y = -t.y;
+        val = cmul(t, make_double2(ck, -cnk));
+      }
+      m = e;
+    }
+    int p = bitrev(m, logn);
+    if (STRIDED)
+      sfft[(long long)p * W + line] = val;
+    else
+      sfft[(long long)line * n + p] = val;
+  }
+  __syncthreads();
+  smem_fft<STRIDED>(sfft, n, logn, W, tw, DIR < 0);
+  const double inv_n = 1.0 / n;
+  for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
+    int line, e;
+    if (STRIDED) {
+      line = q % W;
+      e = q / W;
+    } else {
+      line = q / n;
+      e = q - line * n;
+    }
+    if (line >= nl) continue;
+    double r;
+    if (DIR > 0) {
+      double2 v = STRIDED ? sfft[(long long)e * W + line] : sfft[(long long)line * n + e];
+      double2 t = __ldg(dtw + e);
+      r = t.x * v.x - t.y * v.y;  // Re(dtw * V)
+    } else {
+      // x[2m] = v[m], x[2m+1] = v[n-1-m]
+      int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
+      double2 v = STRIDED ? sfft[(long long)m * W + line] : sfft[(long long)line * n + m];
+      r = v.x * inv_n;
+    }
+    out[base + line * lstride + (long long)e * g.es] = r;
+  }
+}
+
+// dense transform of every line: out[line, k] = sum_e M[k*n + e] in[line, e]
+static __global__ void __launch_bounds__(256) k_dense_lines(const double* __restrict__ in, double* __restrict__ out, LineGeom g,
+                                                            const double* __restrict__ M) {
+  const long long nlines = (long long)g.nx * g.nouter;
+  const long long total = nlines * g.n;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    long long line = q % nlines;
+    int k = (int)(q / nlines);
+    long long x = line % g.nx, o = line / g.nx;
+    long long base = x + o * g.os;
+    const double* Mk = M + (long long)k * g.n;
+    double acc = 0.0;
+    for (int e = 0; e < g.n; ++e) acc = fma(__ldg(Mk + e), in[base + (long long)e * g.es], acc);
+    out[base + (long long)k * g.es] = acc;
+  }
+}
+
+// divide by the symbol
+static __global__ void __launch_bounds__(256) k_sh_symbol_div(double* __restrict__ a, int nx, int ny, int nz,
+                                                              const double* __restrict__ lx, const double* __restrict__ ly,
+                                                              const double* __restrict__ lz, double shift) {
+  const long long total = (long long)nx * ny * nz;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(q % nx), j = (int)((q / nx) % ny), k = (int)(q / ((long long)nx * ny));
+    double t = 1.0 + lx[i] + ly[j] + (lz ? lz[k] : 0.0);
+    a[q] = a[q] / (t * t + shift);
+  }
+}
+static __global__ void __launch_bounds__(256) k_helmholtz_symbol_div(double* __restrict__ a, int nx, int ny, long long nblocks,
+                                                                     const double* __restrict__ lx,
+                                                                     const double* __restrict__ ly, double a0, double a1) {
+  const long long n = (long long)nx * ny, total = n * nblocks;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    long long g = q % n;
+    int i = (int)(g % nx), j = (int)(g / nx);
+    a[q] = a[q] / (a0 + a1 * (lx[i] + ly[j]));
+  }
+}
+
+// Thomas solve with precomputed factors: tri = [cprime (n) | denom_inv (n) | lower (n)]
+static __global__ void k_thomas(const double* __restrict__ tri, const double* __restrict__ in, double* __restrict__ out, int n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double* cp = tri;
+  const double* di = tri + n;
+  const double* lo = tri + 2 * n;
+  double prev = in[0] * di[0];
+  out[0] = prev;
+  for (int i = 1; i < n; ++i) {
+    prev = (in[i] - lo[i] * prev) * di[i];
+    out[i] = prev;
+  }
+  for (int i = n - 2; i >= 0; --i) out[i] -= cp[i] * out[i + 1];
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static bool is_pow2(long long n) { return n >= 8 && n <= 4096 && (n & (n - 1)) == 0; }
+static int ilog2(long long n) {
+  int l = 0;
+  while ((1LL << l) < n) ++l;
+  return l;
+}
+static inline int lin_grid(bk_ctx* c, long long n) {
+  long long g = (n + 255) / 256, cap = (long long)c->nsm * 8;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+static int upload(bk_ctx* c, void** dst, const void* src, size_t bytes) {
+  if (*dst) cudaFree(*dst);
+  BK_CUDA(c, cudaMalloc(dst, bytes));
+  BK_CUDA(c, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return BK_OK;
+}
+
+// transform tables for dimension d of length n. type 0: DCT-II (Neumann), 1: DST-I (Dirichlet; dense only)
+static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type) {
+  Precond& pc = c->pc;
+  std::vector<double> lam(n);
+  const long double PI = 3.14159265358979323846264338327950288L;
+  for (long long k = 0; k < n; ++k)
+    lam[k] = (type == 0) ? (double)((2.0L * cosl(PI * k / n) - 2.0L)) * inv_h2
+                         : (double)(-(2.0L - 2.0L * cosl(PI * (k + 1) / (n + 1)))) * inv_h2;
+  BK_TRY(upload(c, (void**)&pc.lam[d], lam.data(), 8 * n));
+  pc.pow2[d] = (type == 0 && is_pow2(n)) ? 1 : 0;
+  if (pc.pow2[d]) {
+    std::vector<double2> tw(n / 2), dtw(n);
+    for (long long k = 0; k < n / 2; ++k) tw[k] = make_double2((double)cosl(-2.0L * PI * k / n), (double)sinl(-2.0L * PI * k / n));
+    for (long long k = 0; k < n; ++k) dtw[k] = make_double2((double)cosl(-PI * k / (2.0L * n)), (double)sinl(-PI * k / (2.0L * n)));
+    BK_TRY(upload(c, (void**)&pc.tw[d], tw.data(), 16 * (n / 2)));
+    BK_TRY(upload(c, (void**)&pc.dtw[d], dtw.data(), 16 * n));
+  } else {
+    // dense forward F (n x n) followed by dense inverse Finv (n x n)
+    std::vector<double> M(2 * n * n);
+    for (long long k = 0; k < n; ++k)
+      for (long long e = 0; e < n; ++e) {
+        if (type == 0) {
+          long double cv = cosl(PI * (2 * e + 1) * k / (2.0L * n));
+          M[k * n + e] = (double)cv;                                        // C[k] = sum_e x[e] cos(pi (2e+1) k / 2n)
+          M[n * n + e * n + k] = (double)((k == 0 ? 1.0L : 2.0L) * cv / n);  // x[e] = (C0 + 2 sum_k>0 C[k] cos)/n
+        } else {
+          long double sv = sinl(PI * (e + 1) * (k + 1) / (n + 1.0L)) * sqrtl(2.0L / (n + 1.0L));
+          M[k * n + e] = (double)sv;  // orthonormal DST-I is its own inverse
+          M[n * n + e * n + k] = (double)sv;
+        }
+      }
+    BK_TRY(upload(c, (void**)&pc.dense[d], M.data(), 8 * 2 * n * n));
+  }
+  return BK_OK;
+}
+
 extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a1) {
   if (!c) return BK_ERR_ARG;
-  if (kind == BK_PC_NONE) { c->pc.kind = BK_PC_NONE; return BK_OK; }
-  return bk_fail(c, BK_ERR_ARG, "preconditioner kind not implemented", __FILE__, __LINE__);
+  BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  Precond& pc = c->pc;
+  if (kind == BK_PC_NONE) {
+    pc.kind = BK_PC_NONE;
+    return BK_OK;
+  }
+  if (!pc.work) BK_CUDA(c, cudaMalloc(&pc.work, 8 * (size_t)c->ld));
+  if (!pc.work2) BK_CUDA(c, cudaMalloc(&pc.work2, 8 * (size_t)c->ld));
+  if (kind == BK_PC_SH_DCT) {
+    BK_CHECK(c, c->kind == BK_SH2D || c->kind == BK_SH3D, "BK_PC_SH_DCT needs a Swift-Hohenberg context");
+    int nd = c->kind == BK_SH3D ? 3 : 2;
+    for (int d = 0; d < nd; ++d) {
+      double h = 2 * c->lengths[d] / c->dims[d];
+      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 0));
+    }
+  } else if (kind == BK_PC_CGL_DST) {
+    BK_CHECK(c, c->kind == BK_CGL2D || c->kind == BK_POTRAP_CGL2D, "BK_PC_CGL_DST needs a cGL context");
+    for (int d = 0; d < 2; ++d) {
+      double h = 2 * c->lengths[d] / c->dims[d];
+      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1));
+    }
+  } else if (kind == BK_PC_CHAN_TRIDIAG) {
+    BK_CHECK(c, c->kind == BK_CHAN, "BK_PC_CHAN_TRIDIAG needs a chan context");
+    long long n = c->N;
+    double s = (double)(n - 1) * (double)(n - 1);
+    std::vector<double> lo(n, s), di(n, -2 * s), up(n, s), tri(3 * n);
+    di[0] = 1;
+    up[0] = 0;
+    lo[n - 1] = 0;
+    di[n - 1] = 1;  // P[1,1:2] = [1,0]; P[end,end-1:end] = [0,1]  (chan.jl:109)
+    lo[0] = 0;
+    up[n - 1] = 0;
+    // forward elimination factors
+    double denom = di[0];
+    tri[n + 0] = 1.0 / denom;
+    tri[0] = up[0] / denom;
+    for (long long i = 1; i < n; ++i) {
+      denom = di[i] - lo[i] * tri[i - 1];
+      tri[n + i] = 1.0 / denom;
+      tri[i] = up[i] / denom;
+      tri[2 * n + i] = lo[i];
+    }
+    BK_TRY(upload(c, (void**)&pc.tri, tri.data(), 8 * 3 * n));
+  } else {
+    return bk_fail(c, BK_ERR_ARG, "unknown preconditioner kind", __FILE__, __LINE__);
+  }
+  pc.kind = kind;
+  pc.a0 = a0;
+  pc.a1 = a1;
+  return BK_OK;
 }
+
+// one 1-D transform pass along dimension d over `nblocks` consecutive blocks of nx*ny(*nz) values
+static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* out, int nx, int ny, int nz) {
+  Precond& pc = c->pc;
+  LineGeom g;
+  const int dims[3] = {nx, ny, nz};
+  g.n = dims[d];
+  if (d == 0) {
+    g.es = 1;
+    g.nx = 1;
+    g.os = nx;
+    g.nouter = ny * nz;
+  } else if (d == 1) {
+    g.es = nx;
+    g.nx = nx;
+    g.os = (long long)nx * ny;
+    g.nouter = nz;
+  } else {
+    g.es = (long long)nx * ny;
+    g.nx = nx;
+    g.os = nx;
+    g.nouter = ny;
+  }
+  if (pc.pow2[d]) {
+    int W = 4096 / g.n;
+    if (W < 1) W = 1;
+    if (W > 16) W = 16;
+    size_t sm = sizeof(double2) * (size_t)g.n * W;
+    int logn = ilog2(g.n);
+    if (d == 0) {
+      auto kern = dir > 0 ? k_dct_lines<false, 1> : k_dct_lines<false, -1>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      int grid = (g.nouter + W - 1) / W;
+      kern<<<grid, 256, sm, c->stream>>>(in, out, g, logn, W, pc.tw[d], pc.dtw[d]);
+    } else {
+      auto kern = dir > 0 ? k_dct_lines<true, 1> : k_dct_lines<true, -1>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      dim3 grid((g.nx + W - 1) / W, g.nouter);
+      kern<<<grid, 256, sm, c->stream>>>(in, out, g, logn, W, pc.tw[d], pc.dtw[d]);
+    }
+  } else {
+    const double* M = pc.dense[d] + (dir > 0 ? 0 : (size_t)g.n * g.n);
+    LineGeom gg = g;
+    if (d == 0) {  // express x-lines in the (x, outer) form used by the dense kernel: x index is the line element
+      gg.nx = 1;
+      gg.os = nx;
+      gg.nouter = ny * nz;
+    }
+    long long total = (long long)nx * ny * nz;
+    k_dense_lines<<<lin_grid(c, total), 256, 0, c->stream>>>(in, out, gg, M);
+  }
+  c->stats.kernel_launches++;
+  BK_CUDA(c, cudaGetLastError());
+  return BK_OK;
+}
+
 int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) {
-  return bk_fail(c, BK_ERR_STATE, "no preconditioner set up", __FILE__, __LINE__);
+  Precond& pc = c->pc;
+  BK_CHECK(c, pc.kind != BK_PC_NONE, "no preconditioner set up (bk_precond_setup)");
+  BK_CHECK(c, in != out, "preconditioner: in-place application is not supported");
+  const long long N = c->N;
+  if (pc.kind == BK_PC_SH_DCT) {
+    const int nx = (int)c->dims[0], ny = (int)c->dims[1], nz = c->kind == BK_SH3D ? (int)c->dims[2] : 1;
+    const int nd = c->kind == BK_SH3D ? 3 : 2;
+    double* A = pc.work;
+    double* B = pc.work2;
+    BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
+    BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
+    double* cur = B;
+    double* oth = A;
+    if (nd == 3) {
+      BK_TRY(transform_pass(c, 2, +1, B, A, nx, ny, nz));
+      cur = A;
+      oth = B;
+    }
+    k_sh_symbol_div<<<lin_grid(c, N), 256, 0, c->stream>>>(cur, nx, ny, nz, pc.lam[0], pc.lam[1], nd == 3 ? pc.lam[2] : nullptr,
+                                                          pc.a0);
+    c->stats.kernel_launches++;
+    BK_CUDA(c, cudaGetLastError());
+    if (nd == 3) {
+      BK_TRY(transform_pass(c, 2, -1, cur, oth, nx, ny, nz));
+      std::swap(cur, oth);
+    }
+    BK_TRY(transform_pass(c, 1, -1, cur, oth, nx, ny, nz));
+    BK_TRY(transform_pass(c, 0, -1, oth, out, nx, ny, nz));
+  } else if (pc.kind == BK_PC_CGL_DST) {
+    const int nx = (int)c->dims[0], ny = (int)c->dims[1];
+    const long long nblk = (c->kind == BK_POTRAP_CGL2D) ? 2 * c->dims[2] : 2;  // components x slices
+    double* A = pc.work;
+    double* B = pc.work2;
+    BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, (int)nblk));
+    BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, (int)nblk));
+    k_helmholtz_symbol_div<<<lin_grid(c, (long long)nx * ny * nblk), 256, 0, c->stream>>>(B, nx, ny, nblk, pc.lam[0], pc.lam[1],
+                                                                                         pc.a0, pc.a1);
+    c->stats.kernel_launches++;
+    BK_CUDA(c, cudaGetLastError());
+    BK_TRY(transform_pass(c, 1, -1, B, A, nx, ny, (int)nblk));
+    BK_TRY(transform_pass(c, 0, -1, A, out, nx, ny, (int)nblk));
+    if (c->kind == BK_POTRAP_CGL2D) BK_CUDA(c, cudaMemcpyAsync(out + N - 1, in + N - 1, 8, cudaMemcpyDeviceToDevice, c->stream));
+  } else if (pc.kind == BK_PC_CHAN_TRIDIAG) {
+    k_thomas<<<1, 32, 0, c->stream>>>(pc.tri, in, out, (int)N);
+    c->stats.kernel_launches++;
+    BK_CUDA(c, cudaGetLastError());
+  }
+  if (n > N) BK_CUDA(c, cudaMemcpyAsync(out + N, in + N, 8 * (size_t)(n - N), cudaMemcpyDeviceToDevice, c->stream));
+  return BK_OK;
 }
+
 extern "C" int32_t bk_precond_apply(bk_ctx* c, const double* in, double* out) {
   if (!c) return BK_ERR_ARG;
-  return bk_fail(c, BK_ERR_STATE, "no preconditioner set up", __FILE__, __LINE__);
+  double *din, *dout;
+  BK_TRY(bk_stage_in(c, in, c->N, 10, true, &din));
+  BK_TRY(bk_stage_in(c, out, c->N, 11, false, &dout));
+  BK_TRY(bk_precond_apply_dev(c, din, dout, c->N));
+  return bk_stage_out(c, out, c->N, dout);
 }

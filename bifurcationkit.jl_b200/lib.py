@@ -24,7 +24,7 @@ SYMBOLS = [
     "bk_vec_axpby", "bk_vec_dot", "bk_vec_norm2", "bk_vec_norminf", "bk_vec_diffdot",
     "bk_residual", "bk_jac_set_state", "bk_jvp", "bk_precond_setup", "bk_precond_apply",
     "bk_gmres", "bk_gmres2", "bk_bls_bordering", "bk_bls_matrixfree", "bk_bls_map",
-    "bk_eigs_shift_invert", "bk_potrap_set_section",
+    "bk_eigs_shift_invert", "bk_potrap_set_section", "bk_hessenberg_eig",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
         "bk_eigs_shift_invert": [C.c_void_p, dbl, i32, i32, dbl, i32, C.POINTER(GmresOpts), vp, dp, dp, vp,
                                  C.POINTER(i32), C.POINTER(i32)],
         "bk_potrap_set_section": [C.c_void_p, vp, vp],
+        "bk_hessenberg_eig": [dp, i32, i32, dp, dp, dp, dp],
     }
     for name, args in sig.items():
         f = getattr(lib, name)

@@ -1,0 +1,356 @@
+"""Host side of the hot path: Newton, newton_palc and the PALC continuation loop, driving the device
+kernels through the plugin mirror in core.py.  In the reference this layer is Julia and stays Julia
+(src/Newton.jl:66-114, src/continuation/Palc.jl:112-305, src/Continuation.jl:349-504, 506-601,
+src/continuation/Contbase.jl:69-102, src/continuation/Tangents.jl:8-42,71-104,
+src/continuation/Natural.jl:36-58); it is restated here because no Julia toolchain exists in this image
+(julia/BK200.jl is the adapter a maintainer would load instead).
+
+The state vector is either a ``DeviceVec`` (device-resident, "option B") or a NumPy array (host
+buffers crossing the C ABI on every call, "option A"): the loop below is written against the small
+vector interface ``V`` and never touches elements.
+"""
+from dataclasses import dataclass, field
+import math
+
+import numpy as np
+
+from .core import DeviceVec
+
+SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # src/Problems.jl:69
+
+
+class V:
+    """VectorInterface subset (src/BorderedArrays.jl:86-217) for DeviceVec and ndarray."""
+
+    @staticmethod
+    def copy(x):
+        return x.copy()
+
+    @staticmethod
+    def copyto(dst, src):
+        if isinstance(dst, DeviceVec):
+            dst.copyto(src)
+        else:
+            dst[...] = src
+        return dst
+
+    @staticmethod
+    def axpby(y, a, x, b=1.0):
+        """y <- a x + b y (VI.add!)"""
+        if isinstance(y, DeviceVec):
+            return y.axpby_(a, x, b)
+        y *= b
+        y += a * x
+        return y
+
+    @staticmethod
+    def scale(x, a):
+        """x <- a x (VI.scale!)"""
+        if isinstance(x, DeviceVec):
+            return x.scale_(a)
+        x *= a
+        return x
+
+    @staticmethod
+    def dot(x, y):
+        return x.dot(y) if isinstance(x, DeviceVec) else float(np.dot(x, y))
+
+    @staticmethod
+    def diffdot(x, x0, tau):
+        return x.diffdot(x0, tau) if isinstance(x, DeviceVec) else float(np.dot(x - x0, tau))
+
+    @staticmethod
+    def norm2(x):
+        return x.norm() if isinstance(x, DeviceVec) else float(np.linalg.norm(x))
+
+    @staticmethod
+    def norminf(x):
+        return x.norminf() if isinstance(x, DeviceVec) else float(np.max(np.abs(x)))
+
+    @staticmethod
+    def zeros_like(x):
+        return x.copy().zero_() if isinstance(x, DeviceVec) else np.zeros_like(x)
+
+
+norminf = V.norminf
+norm2 = V.norm2
+
+
+@dataclass
+class NewtonPar:
+    """src/Newton.jl:17-33"""
+    tol: float = 1e-10
+    max_iterations: int = 25
+    linsolver: object = None
+    eigsolver: object = None
+
+
+@dataclass
+class ContinuationPar:
+    """src/ContParameters.jl:44-100 (fields the hot path reads)"""
+    dsmin: float = 1e-4
+    dsmax: float = 1e-1
+    ds: float = 1e-2
+    a: float = 0.5
+    p_min: float = -1.0
+    p_max: float = 1.0
+    max_steps: int = 400
+    newton_options: NewtonPar = field(default_factory=NewtonPar)
+    eta: float = 150.0
+    nev: int = 3
+    detect_bifurcation: int = 0
+    tol_stability: float = 1e-10
+
+
+@dataclass
+class PALC:
+    """src/continuation/Palc.jl:70-84"""
+    tangent: str = "secant"
+    theta: float = 0.5
+    bls: object = None
+
+
+class BifurcationProblemB200:
+    """BifurcationProblem whose F and J are the context's device kernels; `lens` = index of the
+    continuation parameter inside the context's parameter tuple (the @optic of the reference)."""
+
+    def __init__(self, ctx, u0, params, lens=0, record=None, delta=SQRT_EPS):
+        self.ctx, self.u0, self.params, self.lens, self.delta = ctx, u0, list(params), lens, delta
+        self.p0 = float(params[lens])
+        self.record = record or V.norm2  # record_from_solution default = norm(x) (src/Problems.jl:286)
+
+    def _set(self, p):
+        q = list(self.params)
+        q[self.lens] = p
+        self.ctx.set_params(q)
+
+    def F(self, x, p, out=None):
+        self._set(p)
+        return self.ctx.residual(x, out)
+
+    def J(self, x, p):
+        self._set(p)
+        return self.ctx.jacobian(x)
+
+
+@dataclass
+class NonLinearSolution:
+    u: object
+    p: float
+    residuals: list
+    converged: bool
+    itnewton: int
+    itlineartot: int
+
+
+def newton(prob, x0, p, opts, normN=V.norm2):
+    """src/Newton.jl:66-114"""
+    x = V.copy(x0)
+    fx = prob.F(x, p)
+    res = normN(fx)
+    residuals = [res]
+    step = itlin = 0
+    while step < opts.max_iterations and res > opts.tol:
+        J = prob.J(x, p)
+        u, cv, it = opts.linsolver(J, fx)
+        itlin += int(np.sum(it))
+        V.axpby(x, -1.0, u, 1.0)  # minus!!(x, u)
+        fx = prob.F(x, p, out=fx)
+        res = normN(fx)
+        residuals.append(res)
+        step += 1
+    return NonLinearSolution(x, p, residuals, residuals[-1] < opts.tol, step, itlin)
+
+
+def _dot_theta(u1, u2, p1, p2, theta):
+    return V.dot(u1, u2) / len(u1) * theta + p1 * p2 * (1.0 - theta)
+
+
+def solve_bls_palc(bls, theta, tau_u, tau_p, J, dR, R, n):
+    """src/LinearBorderSolver.jl:16-36: xiu = theta, xip = 1 - theta, dotp = dot / N"""
+    return bls(J, dR, tau_u, tau_p, R, n, theta, 1.0 - theta, shift=None, dotscale=1.0 / len(R))
+
+
+def newton_palc(prob, z0u, z0p, tau_u, tau_p, zpred_u, zpred_p, ds, theta, contpar, bls, normN=V.norm2):
+    """src/continuation/Palc.jl:187-305 (linesearch = false)."""
+    opts = contpar.newton_options
+    eps = prob.delta
+    N = len(z0u)
+
+    def Nfun(u, p):  # arc_length_eq, Palc.jl:44-56
+        return theta * V.diffdot(u, z0u, tau_u) / N + (1.0 - theta) * (p - z0p) * tau_p - ds
+
+    x = V.copy(zpred_u)
+    p = zpred_p
+    res_f = prob.F(x, p)
+    res_n = Nfun(x, p)
+    dFdp = V.zeros_like(x)
+    res = max(normN(res_f), abs(res_n))
+    residuals = [res]
+    step = itlin = 0
+    while step < opts.max_iterations and res > opts.tol:
+        dFdp = prob.F(x, p + eps, out=dFdp)
+        V.axpby(dFdp, -1.0 / eps, res_f, 1.0 / eps)  # (F(x,p+eps) - F(x,p)) / eps
+        J = prob.J(x, p)
+        u, up, flag, it = solve_bls_palc(bls, theta, tau_u, tau_p, J, dFdp, res_f, res_n)
+        itlin += int(np.sum(it))
+        V.axpby(x, -1.0, u, 1.0)
+        p = min(max(p - up, contpar.p_min), contpar.p_max)
+        res_f = prob.F(x, p, out=res_f)
+        res_n = Nfun(x, p)
+        res = max(normN(res_f), abs(res_n))
+        residuals.append(res)
+        step += 1
+    return NonLinearSolution(x, p, residuals, residuals[-1] < opts.tol, step, itlin)
+
+
+def step_size_control(ds, converged, itnewton, contpar):
+    """src/continuation/Contbase.jl:77-102"""
+    if not converged:
+        if abs(ds) <= contpar.dsmin:
+            return ds, True
+        dsnew = math.copysign(max(abs(ds) / 2, contpar.dsmin), ds)
+    else:
+        Nmax = contpar.newton_options.max_iterations
+        factor = (Nmax - itnewton) / Nmax
+        dsnew = ds * (1 + contpar.a * factor**2)
+    dsnew = math.copysign(min(max(abs(dsnew), contpar.dsmin), contpar.dsmax), dsnew)
+    return dsnew, False
+
+
+@dataclass
+class ContState:
+    z_u: object
+    z_p: float
+    zold_u: object
+    zold_p: float
+    tau_u: object
+    tau_p: float
+    zpred_u: object
+    zpred_p: float
+    ds: float
+    step: int = 0
+    converged: bool = True
+    itnewton: int = 0
+    itlinear: int = 0
+    stop: bool = False
+    n_unstable: tuple = (-1, -1)
+    eigvals: object = None
+
+
+def _secant(st, theta):
+    """src/continuation/Tangents.jl:28-42: tau = (z - z_old) * sign(ds) / ||.||_theta (in place)"""
+    V.copyto(st.tau_u, st.z_u)
+    V.axpby(st.tau_u, -1.0, st.zold_u, 1.0)
+    st.tau_p = st.z_p - st.zold_p
+    alpha = math.copysign(1.0, st.ds) / math.sqrt(_dot_theta(st.tau_u, st.tau_u, st.tau_p, st.tau_p, theta))
+    V.scale(st.tau_u, alpha)
+    st.tau_p *= alpha
+
+
+def _bordered_tangent(prob, st, theta, bls):
+    """src/continuation/Tangents.jl:71-104"""
+    eps = prob.delta
+    dFdl = prob.F(st.z_u, st.z_p + eps)
+    f0 = prob.F(st.z_u, st.z_p)
+    V.axpby(dFdl, -1.0 / eps, f0, 1.0 / eps)
+    J = prob.J(st.z_u, st.z_p)
+    tu, tp, flag, it = solve_bls_palc(bls, theta, st.tau_u, st.tau_p, J, dFdl, V.zeros_like(st.z_u), 1.0)
+    alpha = 1.0 / math.sqrt(_dot_theta(tu, tu, tp, tp, theta))
+    alpha *= math.copysign(1.0, _dot_theta(st.tau_u, tu, st.tau_p, tp, theta))
+    V.copyto(st.tau_u, tu)
+    V.scale(st.tau_u, alpha)
+    st.tau_p = tp * alpha
+
+
+def _predict(st):
+    """addtangent! (src/continuation/Tangents.jl:8-15): z_pred = z + ds * tau"""
+    V.copyto(st.zpred_u, st.z_u)
+    V.axpby(st.zpred_u, st.ds, st.tau_u, 1.0)
+    st.zpred_p = st.z_p + st.ds * st.tau_p
+
+
+def continuation(prob, alg, contpar, normC=V.norm2, u1=None, p1=None, verbose=False, callback=None):
+    """src/Continuation.jl:349-504,506-601.  Returns (rows, state); rows mirror ContResult.branch
+    (param, x = record_from_solution, itnewton, itlinear, ds, step, n_unstable; src/Continuation.jl:259-272).
+    With (u1, p1) the branch starts from two points (iterate_from_two_points, :408-456) -- used to seed
+    branch segments on other GPUs."""
+    opts = contpar.newton_options
+    theta, bls = alg.theta, alg.bls
+    p0 = prob.p0
+    if u1 is None:
+        assert contpar.p_min <= p0 <= contpar.p_max
+        sol0 = newton(prob, prob.u0, p0, opts, normC)
+        if not sol0.converged:
+            raise RuntimeError(f"Newton failed to converge for the initial guess: {sol0.residuals}")
+        p1 = p0 + contpar.ds / contpar.eta
+        sol1 = newton(prob, sol0.u, p1, opts, normC)
+        if not sol1.converged:
+            raise RuntimeError("Newton failed to converge for the initial tangent")
+        u0, u1 = sol0.u, sol1.u
+    else:
+        u0 = V.copy(prob.u0)
+    # state.z = z1, z_old = z0 -> secant tangent; then z <- z0 (initialize!, Palc.jl:112-123)
+    st = ContState(z_u=u1, z_p=p1, zold_u=u0, zold_p=p0, tau_u=V.zeros_like(u0), tau_p=0.0,
+                   zpred_u=V.zeros_like(u0), zpred_p=0.0, ds=contpar.ds)
+    _secant(st, theta)
+    st.z_u, st.z_p = V.copy(u0), p0
+    _predict(st)
+    rows = []
+
+    def eig_update():
+        if contpar.detect_bifurcation > 0 and opts.eigsolver is not None:
+            nprev = st.n_unstable[1]
+            nev_ = max(nprev + 5, contpar.nev) if nprev >= 0 else contpar.nev  # src/Utils.jl:78-79
+            J = prob.J(st.z_u, st.z_p)
+            vals = opts.eigsolver(J, nev_)[0]
+            nun = int(np.sum(np.real(vals) > contpar.tol_stability))  # src/Bifurcations.jl:5-18
+            st.n_unstable = (nun, st.n_unstable[0])
+            st.eigvals = vals
+
+    def save():
+        rows.append(dict(param=st.z_p, x=prob.record(st.z_u), itnewton=st.itnewton, itlinear=st.itlinear,
+                         ds=st.ds, step=st.step, n_unstable=st.n_unstable[0]))
+
+    eig_update()
+    save()
+
+    def done():  # src/Continuation.jl:254-257
+        return (st.step <= contpar.max_steps) and ((contpar.p_min < st.z_p < contpar.p_max) or st.step == 0) and not st.stop
+
+    first = True
+    while True:
+        if not first and st.converged and st.step <= contpar.max_steps and st.step > 0:
+            save()
+            if callback is not None and callback(st) is False:
+                st.stop = True
+        first = False
+        if not done():
+            break
+        if st.zpred_p <= contpar.p_min or st.zpred_p >= contpar.p_max:  # Palc.jl:157-160 -> Natural corrector
+            st.zpred_p = min(max(st.zpred_p, contpar.p_min), contpar.p_max)
+            sol = newton(prob, st.zpred_u, st.zpred_p, opts, normC)
+            sol.p = st.zpred_p
+        else:
+            sol = newton_palc(prob, st.z_u, st.z_p, st.tau_u, st.tau_p, st.zpred_u, st.zpred_p, st.ds, theta, contpar,
+                              bls, normC)
+        st.converged, st.itnewton, st.itlinear = sol.converged, sol.itnewton, sol.itlineartot
+        if sol.converged:
+            st.zold_u, st.z_u = st.z_u, st.zold_u  # swap buffers: z_old <- z
+            st.zold_p = st.z_p
+            V.copyto(st.z_u, sol.u)
+            st.z_p = sol.p
+            eig_update()
+            st.step += 1
+        if verbose:
+            print(f"step {st.step} p={st.z_p:.6e} ds={st.ds:.3e} conv={st.converged} itn={st.itnewton} itl={st.itlinear}",
+                  flush=True)
+        if not st.stop:
+            st.ds, st.stop = step_size_control(st.ds, st.converged, st.itnewton, contpar)
+        if st.converged:
+            if alg.tangent == "secant":
+                _secant(st, theta)
+            else:
+                _bordered_tangent(prob, st, theta, bls)
+        _predict(st)
+    return rows, st

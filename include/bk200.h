@@ -136,6 +136,10 @@ int32_t bk_eigs_shift_invert(bk_ctx* ctx, double sigma, int32_t nev, int32_t kry
                              const bk_gmres_opts* inner, const double* v0, double* vals_re, double* vals_im, double* vecs,
                              int32_t* nconv, int32_t* nops);
 
+/* host-only helper of the eigensolver: eigenpairs of a real upper-Hessenberg matrix (column-major, leading
+ * dimension ldh), complex shifted QR + inverse iteration; vec_* are n x n column-major (may be NULL). */
+int32_t bk_hessenberg_eig(const double* H, int32_t n, int32_t ldh, double* wr, double* wi, double* vec_re, double* vec_im);
+
 /* ---- P5: trapezoid periodic-orbit functional over the context's vector field
  *   (BK_POTRAP_CGL2D contexts; x = [x_1..x_M; T], src/periodicorbit/PeriodicOrbitTrapeze.jl:249-330) */
 int32_t bk_potrap_set_section(bk_ctx* ctx, const double* phi, const double* xpi); /* length N-1 each */

@@ -45,3 +45,32 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_hessenberg_eig_golden_5x5():
+    """Host part of the eigensolver (complex shifted QR + inverse iteration) against the reference's golden
+    spectrum, test/linear_solvers/test_linear.jl:595-614 (matrix reduced to Hessenberg form first)."""
+    import numpy as np
+    import scipy.linalg as sla
+    from tests.test_oracle_linear import J5, GOLD5
+    bk = g.load_package()
+    Hh, Q = sla.hessenberg(J5, calc_q=True)
+    vals, vecs = bk.hessenberg_eig(Hh)
+    key = lambda z: (-round(z.real, 9), z.imag)
+    assert np.allclose(sorted(vals, key=key), sorted(GOLD5, key=key), atol=1e-12)
+    for k in range(5):
+        v = Q @ vecs[:, k]
+        assert np.linalg.norm(J5 @ v - vals[k] * v) < 1e-8
+    # random Hessenberg matrices, incl. symmetric tridiagonal (the SH case)
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 40):
+        A = np.triu(rng.standard_normal((n, n)), -1)
+        vals, vecs = bk.hessenberg_eig(A)
+        ref = np.linalg.eigvals(A)
+        assert np.allclose(sorted(vals, key=key), sorted(ref, key=key), atol=1e-9)
+        for k in range(n):
+            assert np.linalg.norm(A @ vecs[:, k] - vals[k] * vecs[:, k]) < 1e-7 * max(1, np.abs(vals).max())
+    T = np.diag(rng.standard_normal(30)) + np.diag(rng.standard_normal(29), 1)
+    T = T + np.triu(T, 1).T
+    vals, _ = bk.hessenberg_eig(T, vectors=False)
+    assert np.allclose(np.sort(vals.real), np.linalg.eigvalsh(T), atol=1e-10) and np.abs(vals.imag).max() < 1e-10

@@ -1,0 +1,175 @@
+"""GPU parity: preconditioner, preconditioned GMRES, Newton / PALC continuation (device-resident and
+host-buffer state), shift-invert eigenvalues -- CUDA path through the C ABI vs the NumPy oracle."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from oracle import problems, krylov, bls as obls, palc as opalc, precond as oprecond
+
+pytestmark = pytest.mark.gpu
+LX, LY = 8 * np.pi, 4 * np.pi / np.sqrt(3)
+
+
+@pytest.fixture(scope="module")
+def bk():
+    return g.load_package()
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("dims", [(64, 32), (151, 100), (128, 20), (512, 256), (32, 16, 8), (22, 22, 22), (128, 128, 16)])
+def test_sh_dct_preconditioner(bk, dims):
+    L = (LX, LY) if len(dims) == 2 else (np.pi, 1.3 * np.pi, 0.7 * np.pi)
+    kind = bk.BK_SH2D if len(dims) == 2 else bk.BK_SH3D
+    ctx = bk.Context(kind, dims, L, krylov_m=4, params=(-0.1, 1.3))
+    r = np.random.default_rng(0).standard_normal(ctx.N)
+    for shift in (1.0, 0.0 if len(dims) == 3 else 0.3):
+        ctx.precond_setup(bk.BK_PC_SH_DCT, shift)
+        ref = oprecond.dct_precond(dims, L, shift)(r)
+        assert _rel(ctx.precond_apply(r), ref) < 1e-11
+        assert _rel(ctx.precond_apply(ctx.to_device(r)).numpy(), ref) < 1e-11
+
+
+def test_chan_tridiag_preconditioner(bk):
+    n = 1000
+    ctx = bk.Context(bk.BK_CHAN, (n,), (1.0,), krylov_m=4, params=(3.3, 0.01))
+    ctx.precond_setup(bk.BK_PC_CHAN_TRIDIAG)
+    r = np.random.default_rng(1).standard_normal(n)
+    assert _rel(ctx.precond_apply(r), oprecond.chan_lu_precond(n)(r)) < 1e-11
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+@pytest.mark.parametrize("orth", ["cgs", "cgs2"])
+def test_preconditioned_gmres_on_sh_jacobian(bk, side, orth):
+    dims = (128, 64)
+    sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
+    u = problems.sh2d_sol0(*dims, LX, LY)
+    rhs = sh.F(u)
+    P = oprecond.dct_precond(dims, (LX, LY), 1.0)
+    kw = dict(Pl=P) if side == "left" else dict(Pr=P)
+    xo, oko, ito = krylov.GMRESIterativeSolvers(reltol=1e-9, restart=150, maxiter=150, **kw)(lambda v: sh.dF(u, v), rhs)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=150, params=(-0.1, 1.3))
+    ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    ls = bk.GMRESB200(reltol=1e-9, restart=150, maxiter=150, Pl=side == "left", Pr=side == "right", orth=orth)
+    x, ok, it = ls(ctx.jacobian(u), rhs)
+    assert ok and oko, (ok, oko, it, ito)
+    assert abs(it - ito) <= 3, (it, ito)
+    assert _rel(x, xo) < 1e-7
+    assert np.linalg.norm(rhs - sh.dF(u, x)) < 1e-6 * np.linalg.norm(rhs)
+
+
+def _sh_setup(bk, dims, device_state):
+    sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
+    P = oprecond.dct_precond(dims, (LX, LY), 1.0)
+    ols = krylov.GMRESIterativeSolvers(reltol=1e-5, restart=100, maxiter=100, N=sh.N, Pl=P)
+    oprob = lambda u0: opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=u0, p0=-0.1)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=100, params=(-0.1, 1.3))
+    ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    ls = bk.GMRESB200(reltol=1e-5, restart=100, maxiter=100, N=sh.N, Pl=True)
+    wrap = (lambda a: ctx.to_device(a)) if device_state else (lambda a: np.array(a))
+    unwrap = (lambda v: v.numpy()) if device_state else (lambda v: v)
+    return sh, ols, oprob, ctx, ls, wrap, unwrap
+
+
+@pytest.mark.parametrize("device_state", [True, False])
+def test_newton_hexagons_and_palc_branch(bk, device_state):
+    """examples/SH2d-fronts.jl:44-86 at 128x64: Newton to hexagons, localized-front guess, 8 PALC steps with
+    BorderingBLS(GMRES + Pl).  Branch rows (param, ||u||) agree with the oracle to Newton tolerance."""
+    P = bk.palc
+    dims = (128, 64)
+    sh, ols, oprob, ctx, ls, wrap, unwrap = _sh_setup(bk, dims, device_state)
+    u0 = problems.sh2d_sol0(*dims, LX, LY)
+    osol = opalc.newton(oprob(u0), u0, -0.1, opalc.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ols), opalc.norminf)
+    prob = P.BifurcationProblemB200(ctx, wrap(u0), (-0.1, 1.3), lens=0)
+    sol = P.newton(prob, prob.u0, -0.1, P.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ls), P.norminf)
+    assert sol.converged and osol.converged
+    assert abs(sol.itnewton - osol.itnewton) <= 1
+    assert _rel(unwrap(sol.u), osol.u) < 1e-6
+    front = problems.sh2d_front_guess(osol.u, *dims, LX, LY)
+    ofront = opalc.newton(oprob(front), front, -0.1, opalc.NewtonPar(tol=1e-8, max_iterations=30, linsolver=ols), opalc.norminf)
+    assert ofront.converged
+    cpo = opalc.ContinuationPar(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0, max_steps=8,
+                                newton_options=opalc.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ols))
+    orows, _ = opalc.continuation(oprob(ofront.u), opalc.PALC(bls=obls.BorderingBLS(ols, check_precision=False)), cpo,
+                                  normC=opalc.norminf)
+    cp = P.ContinuationPar(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0, max_steps=8,
+                           newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls))
+    prob2 = P.BifurcationProblemB200(ctx, wrap(ofront.u), (-0.1, 1.3), lens=0)
+    rows, st = P.continuation(prob2, P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False)), cp, normC=P.norminf)
+    assert len(rows) == len(orows) == 9
+    for r, o in zip(rows, orows):
+        assert abs(r["param"] - o["param"]) < 1e-7 and abs(r["x"] - o["x"]) < 1e-6 * o["x"], (r, o)
+        assert r["itnewton"] == o["itnewton"]
+    # MatrixFreeBLS drives the same branch (src/LinearBorderSolver.jl:404-437)
+    rows2, _ = P.continuation(prob2, P.PALC(bls=bk.MatrixFreeBLSB200(ls)), cp, normC=P.norminf)
+    for r, o in zip(rows2, orows):
+        assert abs(r["param"] - o["param"]) < 1e-6 and abs(r["x"] - o["x"]) < 1e-5 * o["x"], (r, o)
+
+
+def test_chan_continuation_config1(bk):
+    """Config 1 (plumbing): examples/chan.jl:97-118 at N=1e3 -- matrix-free J, GMRES(restart 20, maxiter 10, reltol 1e-5)
+    with Pl = lu(P), PALC(tangent=Bordered(), bls=BorderingBLS(lsp)) -- against the oracle."""
+    P = bk.palc
+    n, beta = 1000, 0.01
+    lsp_o = krylov.GMRESIterativeSolvers(reltol=1e-5, N=n, restart=20, maxiter=10, Pl=oprecond.chan_lu_precond(n))
+    oprob = opalc.Problem(F=lambda x, a: problems.chan_F(x, a, beta), J=lambda x, a: (lambda dx: problems.chan_dF(x, dx, a, beta)),
+                          u0=problems.chan_sol0(n), p0=3.3)
+    kw = dict(dsmin=0.01, dsmax=0.5, ds=0.01, p_max=4.2, p_min=-1.0, max_steps=30)
+    orows, _ = opalc.continuation(oprob, opalc.PALC(tangent="bordered", bls=obls.BorderingBLS(lsp_o)),
+                                  opalc.ContinuationPar(newton_options=opalc.NewtonPar(tol=1e-9, max_iterations=10, linsolver=lsp_o), **kw),
+                                  normC=opalc.norminf)
+    ctx = bk.Context(bk.BK_CHAN, (n,), (1.0,), krylov_m=20, params=(3.3, beta))
+    ctx.precond_setup(bk.BK_PC_CHAN_TRIDIAG)
+    lsp = bk.GMRESB200(reltol=1e-5, N=n, restart=20, maxiter=10, Pl=True)
+    prob = P.BifurcationProblemB200(ctx, ctx.to_device(problems.chan_sol0(n)), (3.3, beta), lens=0)
+    rows, _ = P.continuation(prob, P.PALC(tangent="bordered", bls=bk.BorderingBLSB200(lsp)),
+                             P.ContinuationPar(newton_options=P.NewtonPar(tol=1e-9, max_iterations=10, linsolver=lsp), **kw),
+                             normC=P.norminf)
+    assert len(rows) == len(orows) > 10
+    for r, o in zip(rows, orows):
+        assert abs(r["param"] - o["param"]) < 1e-6 and abs(r["x"] - o["x"]) < 1e-6 * o["x"], (r, o)
+
+
+def test_shift_invert_eigs_sh2d(bk):
+    """src/EigSolver.jl:246-266 with the GMRES inner solver: leading eigenvalues of the SH Jacobian at the
+    hexagon state vs LAPACK on the dense Jacobian (test_linear.jl:666-673 style, tol 1e-7 here because the
+    inner solves are iterative)."""
+    dims = (48, 32)
+    sh, ols, oprob, ctx, ls, wrap, unwrap = _sh_setup(bk, dims, True)
+    u0 = problems.sh2d_sol0(*dims, LX, LY)
+    osol = opalc.newton(oprob(u0), u0, -0.1, opalc.NewtonPar(tol=1e-10, max_iterations=25, linsolver=krylov.DefaultLS()),
+                        opalc.norminf) if False else None
+    J_dense = sh.jac_sparse(u0).toarray()
+    ref = np.sort(np.linalg.eigvalsh(0.5 * (J_dense + J_dense.T)))[::-1]
+    inner = bk.GMRESB200(reltol=1e-11, restart=100, maxiter=100, Pl=True, orth="cgs2")
+    eig = bk.ShiftInvertB200(0.1, inner, krylovdim=40, tol=1e-9, maxrestart=20)
+    J = ctx.jacobian(ctx.to_device(u0))
+    vals, vecs, cv, nops = eig(J, 6, want_vectors=True)
+    assert cv
+    # eigenvalues closest to sigma = 0.1, sorted by decreasing real part
+    near = ref[np.argsort(np.abs(ref - 0.1))[:6]]
+    near = np.sort(near)[::-1]
+    assert np.max(np.abs(vals.real - near)) < 1e-7 and np.max(np.abs(vals.imag)) < 1e-9
+    assert np.all(np.diff(vals.real) <= 1e-12)
+    for k in range(6):
+        v = vecs[:, k]
+        assert np.linalg.norm(J_dense @ v - vals[k].real * v) < 1e-6 * np.linalg.norm(v)
+
+
+def test_shift_invert_eigs_cgl_complex(bk):
+    """Non-symmetric case: cGL linearised at 0 has eigenvalues r + lambda_k(Lap) +- i nu."""
+    dims = (24, 12)
+    gl = problems.GinzburgLandau2D(*dims, np.pi, np.pi / 2, r=1.2)
+    ctx = bk.Context(bk.BK_CGL2D, dims, (np.pi, np.pi / 2), krylov_m=120, params=(1.2, 0.1, 1.0, -1.0, 1.0))
+    J = ctx.jacobian(np.zeros(gl.N))
+    lam = np.sort(np.linalg.eigvalsh(gl.lap.toarray()))[::-1]
+    inner = bk.GMRESB200(reltol=1e-12, restart=120, maxiter=600, orth="cgs2")
+    eig = bk.ShiftInvertB200(0.3, inner, krylovdim=40, tol=1e-9, maxrestart=30)
+    vals, _, cv, _ = eig(J, 4)
+    ref = np.array([1.2 + lam[0] + 1j, 1.2 + lam[0] - 1j, 1.2 + lam[1] + 1j, 1.2 + lam[1] - 1j])
+    # the 4 eigenvalues closest to sigma are the two leading conjugate pairs
+    key = lambda z: (-round(z.real, 7), -z.imag)
+    assert cv
+    assert np.allclose(sorted(vals, key=key), sorted(ref, key=key), atol=1e-6)
