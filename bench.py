@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- continuation steps/sec on 2-D Swift-Hohenberg (SH2d-fronts, fp64) + achieved HBM GB/s of the
+fused JVP+Arnoldi kernel, per BASELINE.json.
+
+A "step" = one PALC continuation step (secant predictor + Newton-Krylov corrector: per Newton iteration
+2 residuals, 1 BorderingBLS solve = 2 GMRES solves with the DCT preconditioner on the right, fused
+JVP+Arnoldi kernels).  N=1 workload: SH2d-fronts 1024^2 (BASELINE.json configs[2] on one GPU; the metric is
+quoted on SH2d 1024^2).  For N>1 the branch is partitioned by continuation step: every rank advances its own
+segment of K steps from a seed produced by a deterministic scout run, state vectors are replicated, and the
+only collective is an all_gather of the (lambda, ||u||, itnewton, itlinear) rows (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 1024] [--impl reference]
+
+--impl reference : times the CPU restatement of the reference path (oracle/, NumPy/SciPy -- Julia is absent
+from this image) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LX, LY = 8 * np.pi, 4 * np.pi / np.sqrt(3)  # examples/SH2d-fronts.jl:10-11
+PAR = (-0.1, 1.3)                            # (l, nu) examples/SH2d-fronts.jl:55
+CONT = dict(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0)  # examples/SH2d-fronts.jl:86
+GMRES = dict(reltol=1e-5, restart=100, maxiter=100)  # examples/SH2d-fronts.jl:122 (reltol), config "GMRES(100)"
+
+
+def sol0(n):
+    X = -LX + 2 * LX / n * np.arange(n)
+    Y = -LY + 2 * LY / n * np.arange(n)
+    s = np.cos(X)[None, :] + np.cos(X / 2)[None, :] * np.cos(np.sqrt(3.0) * Y / 2)[:, None]
+    s = s - s.min()
+    s = s / s.max()
+    return ((s - 0.25) * 1.7).reshape(-1)
+
+
+def front_guess(u_hexa, n):
+    X = -LX + 2 * LX / n * np.arange(n)
+    return 0.4 * u_hexa * np.tile(np.exp(-((X + LX) ** 2) / 25.0), n)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def gpu_setup(bk, n, device, host_state=False):
+    P = bk.palc
+    ctx = bk.Context(bk.BK_SH2D, (n, n), (LX, LY), krylov_m=GMRES["restart"], device=device, params=PAR)
+    ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)  # (L1 + I)^-1, examples/SH2d-fronts.jl:121
+    ls = bk.GMRESB200(N=n * n, Pr=True, **GMRES)
+    wrap = (lambda a: np.array(a)) if host_state else ctx.to_device
+    opt = P.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ls)  # examples/SH2d-fronts.jl:57
+    prob = P.BifurcationProblemB200(ctx, wrap(sol0(n)), PAR, lens=0)
+    hexa = P.newton(prob, prob.u0, PAR[0], opt, P.norminf)
+    assert hexa.converged, hexa.residuals
+    uh = hexa.u if host_state else hexa.u.numpy()
+    prob = P.BifurcationProblemB200(ctx, wrap(front_guess(uh, n)), PAR, lens=0)
+    fr = P.newton(prob, prob.u0, PAR[0], P.NewtonPar(tol=1e-9, max_iterations=30, linsolver=ls), P.norminf)
+    assert fr.converged, fr.residuals
+    return ctx, ls, fr.u
+
+
+def gpu_run(bk, ctx, ls, u_start, p_start, steps, warmup, torch, timing=True, u1=None, p1=None, flush=None):
+    """Runs warmup+steps PALC steps; returns (rows, per-step ms list (CUDA events on the library's stream), stats delta)."""
+    P = bk.palc
+    cp = P.ContinuationPar(max_steps=warmup + steps, newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls),
+                           **CONT)
+    alg = P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False))
+    pars = list(PAR)
+    pars[0] = p_start
+    prob = P.BifurcationProblemB200(ctx, u_start, pars, lens=0)
+    stream = torch.cuda.ExternalStream(ctx.lib.bk_stream(ctx.handle))
+    starts, ends = [], []
+    state = {"n": 0, "s0": None}
+
+    def cb(st):
+        # called at step 0 and after each accepted step: close the running step's event pair, flush L2, open the next
+        k = state["n"]
+        if k > 0:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            ends.append(e)
+        if k == warmup:
+            ctx.sync()
+            ctx.set_timing(timing)
+            state["s0"] = ctx.stats()
+            torch.cuda.profiler.start()  # cudaProfilerStart: lets `ncu --profile-from-start off` see only the timed region
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.zero_()
+        e2 = torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        starts.append(e2)
+        state["n"] += 1
+        return True
+
+    rows, st = P.continuation(prob, alg, cp, normC=P.norminf, u1=u1, p1=p1, callback=cb)
+    ctx.sync()
+    torch.cuda.profiler.stop()
+    ctx.set_timing(False)
+    s1 = ctx.stats()
+    ms = [starts[i].elapsed_time(ends[i]) for i in range(len(ends))]
+    delta = {k: s1[k] - state["s0"][k] for k in s1} if state["s0"] else {}
+    return rows, ms[warmup:], delta, st
+
+
+def cpu_steps(n, u_start, p_start, nsteps, workers):
+    """CPU restatement (oracle/) of the same PALC steps; returns (rows, seconds)."""
+    from oracle import problems, krylov, bls as obls, palc as opalc, precond as oprecond
+    sh = problems.SwiftHohenberg((n, n), (LX, LY), l=PAR[0], nu=PAR[1])
+    Pinv = oprecond.dct_precond((n, n), (LX, LY), 1.0, workers=workers)
+    ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
+    prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=u_start, p0=p_start)
+    cp = opalc.ContinuationPar(max_steps=nsteps, newton_options=opalc.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ols), **CONT)
+    tmark = {}
+
+    def cb(st):
+        tmark.setdefault("t", []).append(time.perf_counter())
+        return True
+
+    t0 = time.perf_counter()
+    rows, st = opalc.continuation(prob, opalc.PALC(bls=obls.BorderingBLS(ols, check_precision=False)), cp, normC=opalc.norminf,
+                                  callback=cb)
+    t1 = time.perf_counter()
+    # the first callback fires at step 0, i.e. after the two start-up Newton solves, which the metric excludes
+    # (src/Continuation.jl:370-393): steps/sec is counted over the continuation! loop only
+    ts = tmark.get("t", [])
+    if len(ts) >= 2:
+        return rows, (ts[-1] - ts[0]), len(ts) - 1
+    return rows, (t1 - t0), 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--grid", type=int, default=1024)
+    ap.add_argument("--impl", default="bk200")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    n = args.grid
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"SH2d-fronts {n}x{n} fp64, PALC (secant) + BorderingBLS + GMRES({GMRES['restart']}) reltol {GMRES['reltol']:g}, Pr = DCT (L1+I)^-1"
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import scipy.fft  # noqa
+        # bounded sample: the CPU path needs a start point on the branch; the hexagon/front Newton solves at full
+        # size take minutes on CPU, so the sample starts from the front guess relaxed on the CPU with the same solver.
+        from oracle import problems, krylov, palc as opalc, precond as oprecond
+        t_setup = time.perf_counter()
+        sh = problems.SwiftHohenberg((n, n), (LX, LY), l=PAR[0], nu=PAR[1])
+        Pinv = oprecond.dct_precond((n, n), (LX, LY), 1.0, workers=cores)
+        ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
+        prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=sol0(n), p0=PAR[0])
+        hexa = opalc.newton(prob, prob.u0, PAR[0], opalc.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ols), opalc.norminf)
+        fr = opalc.newton(prob, front_guess(hexa.u, n), PAR[0], opalc.NewtonPar(tol=1e-9, max_iterations=30, linsolver=ols),
+                          opalc.norminf)
+        t_setup = time.perf_counter() - t_setup
+        k = max(1, min(args.steps, args.cpu_steps))
+        rows, secs, nst = cpu_steps(n, fr.u, PAR[0], k, cores)
+        v = nst / secs
+        print(json.dumps({"metric": "continuation steps/sec (SH2d PALC)", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+                          "steps": nst, "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                          "config": {"workload": workload, "setup_s": round(t_setup, 1)},
+                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                                           "sample": f"{nst} PALC steps from the converged front, NumPy/SciPy oracle (SciPy CSR SpMV 1 thread, "
+                                                     f"BLAS-1 + pocketfft DCT on {cores} threads)"},
+                          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import __graft_entry__ as g
+    bk = g.load_package()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local if world > 1 else 0
+    torch.cuda.set_device(dev)
+    ctx, ls, u_front = gpu_setup(bk, n, dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
+
+    # ---- seeds for N > 1: deterministic scout on every rank (replicated state), segment r starts at scout point r*K
+    u_start, p_start, u1, p1 = u_front, PAR[0], None, None
+    scout_ms = 0.0
+    if world > 1:
+        t0 = time.perf_counter()
+        P = bk.palc
+        seeds = {}
+        stride = args.steps + args.warmup
+
+        def grab(st):
+            if st.step % stride == 0 or (st.step - 1) % stride == 0:
+                seeds[st.step] = (st.z_u.copy(), st.z_p)
+            return st.step < rank * stride + 1
+
+        cp = P.ContinuationPar(max_steps=stride * (world - 1) + 1,
+                               newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls), **CONT)
+        prob = P.BifurcationProblemB200(ctx, u_front, PAR, lens=0)
+        if rank > 0:
+            P.continuation(prob, P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False)), cp, normC=P.norminf, callback=grab)
+            a, b = rank * stride, rank * stride + 1
+            u_start, p_start = seeds[a]
+            u1, p1 = seeds[b]
+        ctx.sync()
+        scout_ms = (time.perf_counter() - t0) * 1e3
+
+    sampler = ClockSampler(dev)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    rows, ms, delta, st = gpu_run(bk, ctx, ls, u_start, p_start, args.steps, args.warmup, torch, timing=True, u1=u1, p1=p1,
+                                  flush=flush)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop()
+    my_ms = float(np.sum(ms))
+    nsteps = len(ms)
+    tt = torch.tensor([my_ms, float(nsteps)], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist:
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        tmax = max(float(t[0]) for t in allt)
+        total_steps = int(sum(float(t[1]) for t in allt))
+        # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear) per batch
+        R = torch.zeros((args.steps + args.warmup + 1, 4), dtype=torch.float64, device=f"cuda:{dev}")
+        for i, r in enumerate(rows[: R.shape[0]]):
+            R[i] = torch.tensor([r["param"], r["x"], r["itnewton"], r["itlinear"]], dtype=torch.float64)
+        allR = [torch.zeros_like(R) for _ in range(world)]
+        dist.all_gather(allR, R)
+        branch = torch.cat(allR).cpu().numpy()
+    else:
+        tmax, total_steps = my_ms, nsteps
+        branch = np.array([[r["param"], r["x"], r["itnewton"], r["itlinear"]] for r in rows])
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    value = total_steps / (tmax * 1e-3)
+    timed_rows = rows[args.warmup + 1:]
+    itn = float(np.mean([r["itnewton"] for r in timed_rows])) if timed_rows else 0.0
+    itl = float(np.mean([r["itlinear"] for r in timed_rows])) if timed_rows else 0.0
+
+    peak, peak_src = measured_peak()
+    fused_ms, fused_b, fused_l = delta.get("total_fused_ms", 0.0), delta.get("total_fused_bytes", 0), delta.get("total_fused_launches", 0)
+    ach = (fused_b / 1e9) / (fused_ms * 1e-3) if fused_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_fused_jvp_dots<2> + k_update_norm (fused JVP+Arnoldi step, 2 launches/step)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src,
+                "traffic": None, "launches": int(fused_l), "avg_launch_us": (fused_ms * 1e3 / fused_l) if fused_l else None,
+                "algorithmic_bytes_per_launch": (fused_b / fused_l) if fused_l else None,
+                "share_of_step": (fused_ms / my_ms) if my_ms else None}
+
+    out = {"metric": "continuation steps/sec (SH2d PALC)", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": tmax / max(1, nsteps), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload, "grid": [n, n], "mean_itnewton": itn, "mean_itlinear_per_step": itl,
+                      "l2": "256 MiB L2 flush between timed steps (outside the event pairs); Krylov basis per solve > L2",
+                      "parallelism": f"branch segments x{world}, replicated state" if world > 1 else "1 GPU",
+                      "scout_ms": scout_ms, "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())]},
+           "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline}
+
+    # ---- e2e: the same steps through the plugin / C ABI with HOST buffers (NumPy state; H2D/D2H inside every call)
+    if not args.no_e2e and world == 1:
+        uh = u_front.numpy()
+        k_e2e = max(2, min(args.steps, 5))
+        rows_h, ms_h, d_h, _ = gpu_run(bk, ctx, ls, uh, PAR[0], k_e2e, 1, torch, timing=False, flush=flush)
+        v = len(ms_h) / (np.sum(ms_h) * 1e-3)
+        out["e2e"] = {"value": v, "unit": "steps/s", "h2d_bytes_per_step": int(d_h["h2d_bytes"] / max(1, len(ms_h))),
+                      "d2h_bytes_per_step": int(d_h["d2h_bytes"] / max(1, len(ms_h))), "steps": len(ms_h),
+                      "note": "state vectors are host NumPy arrays; every residual / bordered solve crosses the C ABI with host pointers"}
+    elif world > 1:
+        out["e2e"] = None
+
+    # ---- cpu_baseline: oracle port on the host cores, bounded sample from the same start point
+    if not args.no_cpu_baseline and world == 1:
+        rows_c, secs, nst = cpu_steps(n, u_front.numpy(), PAR[0], args.cpu_steps, cores)
+        out["cpu_baseline"] = {"value": nst / secs, "unit": "steps/s", "cores": cores, "kind": "port",
+                               "sample": f"{nst} PALC steps of the same branch from the same start point; "
+                                         f"NumPy/SciPy oracle: SciPy CSR SpMV with kron-assembled L1 (1 thread), BLAS-1 MGS, pocketfft DCT Pr ({cores} threads)"}
+        # parity of the sample rows with the GPU rows (same step history expected)
+        m = min(len(rows_c), len(rows))
+        out["cpu_baseline"]["max_abs_param_diff_vs_gpu"] = float(max(abs(rows_c[i]["param"] - rows[i]["param"]) for i in range(m)))
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

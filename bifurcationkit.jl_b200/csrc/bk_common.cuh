@@ -93,7 +93,7 @@ struct bk_ctx {
   double* eig_dev = nullptr; // ones (qcap+2) | hcolA (qcap+2) | hcolB (qcap+2) | g (qcap+2) | coef (2*(qcap+2))
   double* eig_pinned = nullptr;
   Precond pc;
-  bk_stats stats = {0, 0, 0, 0.0, 0, 0};
+  bk_stats stats = {0, 0, 0, 0.0, 0, 0, 0.0, 0, 0};
   bool timing = false;
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tpairs;

@@ -368,6 +368,10 @@ static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lon
   BK_CUDA(c, cudaEventRecord(c->events[k], c->stream));
   c->stats.last_fused_bytes += 8LL * n * (2LL * j + 4);
   c->stats.last_fused_launches += 2;
+  if (fuse) {
+    c->stats.total_fused_bytes += 8LL * n * (2LL * j + 4);
+    c->stats.total_fused_launches += 2;
+  }
   return BK_OK;
 }
 
@@ -505,6 +509,7 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
       if (cudaEventElapsedTime(&t, c->tpairs[i].first, c->tpairs[i].second) == cudaSuccess) ms += t;
     }
     c->stats.last_fused_ms = ms;
+    if (o->fused && fused_available(op) && !(o->pc_side == BK_SIDE_LEFT && c->pc.kind != BK_PC_NONE)) c->stats.total_fused_ms += ms;
   }
   if (converged) *converged = conv ? 1 : 0;
   if (iters) *iters = total;

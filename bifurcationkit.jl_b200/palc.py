@@ -314,6 +314,8 @@ def continuation(prob, alg, contpar, normC=V.norm2, u1=None, p1=None, verbose=Fa
 
     eig_update()
     save()
+    if callback is not None and callback(st) is False:  # step 0 (lets callers mark the start of the continuation! loop)
+        st.stop = True
 
     def done():  # src/Continuation.jl:254-257
         return (st.step <= contpar.max_steps) and ((contpar.p_min < st.z_p < contpar.p_max) or st.step == 0) and not st.stop

@@ -71,6 +71,9 @@ typedef struct bk_stats {
   double  last_fused_ms;   /* device time of the fused JVP+Arnoldi kernels in the last bk_gmres call (0 unless timing enabled) */
   int64_t last_fused_bytes;/* algorithmic bytes moved by them, 8N(2j+4) summed over the iterations run */
   int64_t last_fused_launches;
+  double  total_fused_ms;     /* cumulative over all solves that ran the FUSED JVP+Arnoldi kernel (timing enabled) */
+  int64_t total_fused_bytes;  /* cumulative algorithmic bytes of those launches */
+  int64_t total_fused_launches;
 } bk_stats;
 
 /* ---- context --------------------------------------------------------------------------- */

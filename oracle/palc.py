@@ -240,6 +240,8 @@ def continuation(prob, alg, contpar, normC=norm2, u1=None, p1=None, verbose=Fals
 
     eig_update()
     save()  # ContResult(it, state) at step 0 (src/Continuation.jl:322-330)
+    if callback is not None and callback(st) is False:  # step 0 hook (marks the start of the continuation! loop)
+        st.stop = True
 
     def done():
         return (st.step <= contpar.max_steps) and ((contpar.p_min < st.z_p < contpar.p_max) or st.step == 0) and not st.stop

@@ -197,7 +197,7 @@ def test_bls_map_and_bordered_solvers(bk):
     A[N, :N] = xiu * b / N
     A[N, N] = xip * dzp
     ref = np.linalg.solve(A, np.concatenate([R, [n]]))
-    ls = bk.GMRESB200(reltol=1e-12, restart=150, maxiter=150)
+    ls = bk.GMRESB200(reltol=1e-12, restart=150, maxiter=150, orth="cgs2")  # 1e-12 needs re-orthogonalisation
     for solver in (bk.BorderingBLSB200(ls, check_precision=False), bk.BorderingBLSB200(ls, check_precision=True, k=2),
                    bk.MatrixFreeBLSB200(ls)):
         dX, dl, ok, it = solver(J, a, b, dzp, R, n, xiu, xip, shift=shift, dotscale=1.0 / N)
