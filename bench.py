@@ -27,13 +27,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LX, LY = 8 * np.pi, 4 * np.pi / np.sqrt(3)  # examples/SH2d-fronts.jl:10-11
+LX0, LY0 = 8 * np.pi, 4 * np.pi / np.sqrt(3)  # examples/SH2d-fronts.jl:10-11 (151 x 100 grid)
+
+
+def domain(n):
+    """The domain grows with the grid so that the mesh width stays that of the reference's own GPU example
+    (examples/SH2d-fronts-cuda.jl:66-69: Nx = Ny = 512 on lx = 16 pi, ly = 2*2pi/sqrt(3)*2, i.e. the example's
+    lengths x2): lengths = example lengths x n/256.  On the ORIGINAL lengths a 1024^2 grid has hy = 0.014 and the
+    rounding floor of evaluating (I+Lap)^2 u in fp64 (~ eps/hy^4 ~ 4e-8, measured) sits ABOVE the example's Newton
+    tolerances (1e-8 / 1e-9), for the reference's sparse-matrix path just as for the stencil."""
+    s = max(1.0, n / 256.0)
+    return LX0 * s, LY0 * s
+
+
 PAR = (-0.1, 1.3)                            # (l, nu) examples/SH2d-fronts.jl:55
 CONT = dict(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0)  # examples/SH2d-fronts.jl:86
 GMRES = dict(reltol=1e-5, restart=100, maxiter=100)  # examples/SH2d-fronts.jl:122 (reltol), config "GMRES(100)"
 
 
 def sol0(n):
+    LX, LY = domain(n)
     X = -LX + 2 * LX / n * np.arange(n)
     Y = -LY + 2 * LY / n * np.arange(n)
     s = np.cos(X)[None, :] + np.cos(X / 2)[None, :] * np.cos(np.sqrt(3.0) * Y / 2)[:, None]
@@ -43,6 +56,7 @@ def sol0(n):
 
 
 def front_guess(u_hexa, n):
+    LX, LY = domain(n)
     X = -LX + 2 * LX / n * np.arange(n)
     return 0.4 * u_hexa * np.tile(np.exp(-((X + LX) ** 2) / 25.0), n)
 
@@ -95,7 +109,7 @@ def measured_peak():
 # ----------------------------------------------------------------------------------------------- GPU arm
 def gpu_setup(bk, n, device, host_state=False):
     P = bk.palc
-    ctx = bk.Context(bk.BK_SH2D, (n, n), (LX, LY), krylov_m=GMRES["restart"], device=device, params=PAR)
+    ctx = bk.Context(bk.BK_SH2D, (n, n), domain(n), krylov_m=GMRES["restart"], device=device, params=PAR)
     ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)  # (L1 + I)^-1, examples/SH2d-fronts.jl:121
     ls = bk.GMRESB200(N=n * n, Pr=True, **GMRES)
     wrap = (lambda a: np.array(a)) if host_state else ctx.to_device
@@ -157,8 +171,8 @@ def gpu_run(bk, ctx, ls, u_start, p_start, steps, warmup, torch, timing=True, u1
 def cpu_steps(n, u_start, p_start, nsteps, workers):
     """CPU restatement (oracle/) of the same PALC steps; returns (rows, seconds)."""
     from oracle import problems, krylov, bls as obls, palc as opalc, precond as oprecond
-    sh = problems.SwiftHohenberg((n, n), (LX, LY), l=PAR[0], nu=PAR[1])
-    Pinv = oprecond.dct_precond((n, n), (LX, LY), 1.0, workers=workers)
+    sh = problems.SwiftHohenberg((n, n), domain(n), l=PAR[0], nu=PAR[1])
+    Pinv = oprecond.dct_precond((n, n), domain(n), 1.0, workers=workers)
     ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
     prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=u_start, p0=p_start)
     cp = opalc.ContinuationPar(max_steps=nsteps, newton_options=opalc.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ols), **CONT)
@@ -195,7 +209,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"SH2d-fronts {n}x{n} fp64, PALC (secant) + BorderingBLS + GMRES({GMRES['restart']}) reltol {GMRES['reltol']:g}, Pr = DCT (L1+I)^-1"
+    workload = f"SH2d-fronts {n}x{n} fp64 on (lx, ly) = {n / 256:g} x (8 pi, 4 pi/sqrt 3), PALC (secant) + BorderingBLS + GMRES({GMRES['restart']}) reltol {GMRES['reltol']:g}, Pr = DCT (L1+I)^-1"
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -206,8 +220,8 @@ def main():
         # size take minutes on CPU, so the sample starts from the front guess relaxed on the CPU with the same solver.
         from oracle import problems, krylov, palc as opalc, precond as oprecond
         t_setup = time.perf_counter()
-        sh = problems.SwiftHohenberg((n, n), (LX, LY), l=PAR[0], nu=PAR[1])
-        Pinv = oprecond.dct_precond((n, n), (LX, LY), 1.0, workers=cores)
+        sh = problems.SwiftHohenberg((n, n), domain(n), l=PAR[0], nu=PAR[1])
+        Pinv = oprecond.dct_precond((n, n), domain(n), 1.0, workers=cores)
         ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
         prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=sol0(n), p0=PAR[0])
         hexa = opalc.newton(prob, prob.u0, PAR[0], opalc.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ols), opalc.norminf)

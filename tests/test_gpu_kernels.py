@@ -183,7 +183,7 @@ def test_bls_map_and_bordered_solvers(bk):
     a, b, R = rng.standard_normal(N), rng.standard_normal(N), rng.standard_normal(N)
     c, n = 0.37, -0.81
     x = rng.standard_normal(N + 1)
-    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=150, params=(-0.1, 1.3))
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=400, params=(-0.1, 1.3))
     J = ctx.jacobian(u)
     Jd = sh.jac_sparse(u).toarray()
     for shift in (None, 2.5):
@@ -197,7 +197,7 @@ def test_bls_map_and_bordered_solvers(bk):
     A[N, :N] = xiu * b / N
     A[N, N] = xip * dzp
     ref = np.linalg.solve(A, np.concatenate([R, [n]]))
-    ls = bk.GMRESB200(reltol=1e-12, restart=150, maxiter=150, orth="cgs2")  # 1e-12 needs re-orthogonalisation
+    ls = bk.GMRESB200(reltol=1e-12, restart=400, maxiter=400, orth="cgs2")  # cond(J - 3I) ~ 200 on this grid  # 1e-12 needs re-orthogonalisation
     for solver in (bk.BorderingBLSB200(ls, check_precision=False), bk.BorderingBLSB200(ls, check_precision=True, k=2),
                    bk.MatrixFreeBLSB200(ls)):
         dX, dl, ok, it = solver(J, a, b, dzp, R, n, xiu, xip, shift=shift, dotscale=1.0 / N)
