@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/bk200.h"
 
@@ -87,6 +88,9 @@ struct bk_ctx {
   double* host_pinned = nullptr; // pinned bounce buffer (ld doubles) for pageable host memory
   // generic temporaries for BLS/eigs
   std::vector<double*> tmp;
+  // bk_vec_alloc pool: live allocations (ptr -> padded length) and the recycled free list
+  std::unordered_map<double*, size_t> vec_live;
+  std::vector<std::pair<size_t, double*>> vec_pool;
   // eigensolver workspace (lazily allocated)
   double* Q = nullptr;       // (qcap+1) x ld Arnoldi basis of the shift-invert operator
   int qcap = 0;

@@ -84,7 +84,7 @@ extern "C" int32_t bk_ctx_create(int32_t device, int32_t kind, const int64_t dim
   BK_CHECK(c, krylov_m >= 1 && krylov_m <= 1024, "krylov_m out of range");
   c->N = n;
   c->m = krylov_m;
-  c->ld = ((n + 1 + 31) / 32) * 32;
+  c->ld = ((n + 2 + 31) / 32) * 32;  // >= N + 2: bordered vectors (N+1) keep one zero pad element for even-sized TMA rows
   BK_CUDA(c, cudaSetDevice(device));
   cudaDeviceProp prop;
   BK_CUDA(c, cudaGetDeviceProperties(&prop, device));
@@ -96,6 +96,11 @@ extern "C" int32_t bk_ctx_create(int32_t device, int32_t kind, const int64_t dim
   BK_CUDA(c, cudaMalloc(&c->w, 8 * ld));
   BK_CUDA(c, cudaMalloc(&c->z, 8 * ld));
   BK_CUDA(c, cudaMalloc(&c->r, 8 * ld));
+  BK_CUDA(c, cudaMemset(c->u_state, 0, 8 * ld));
+  BK_CUDA(c, cudaMemset(c->V, 0, 8 * ld * (m + 1)));
+  BK_CUDA(c, cudaMemset(c->w, 0, 8 * ld));
+  BK_CUDA(c, cudaMemset(c->z, 0, 8 * ld));
+  BK_CUDA(c, cudaMemset(c->r, 0, 8 * ld));
   BK_CUDA(c, cudaMalloc(&c->scales, 8 * (m + 4)));
   BK_CUDA(c, cudaMalloc(&c->gcoef, 8 * (m + 4)));
   BK_CUDA(c, cudaMalloc(&c->hcols, 8 * (m + 1) * (m + 4)));
@@ -104,7 +109,7 @@ extern "C" int32_t bk_ctx_create(int32_t device, int32_t kind, const int64_t dim
   BK_CUDA(c, cudaMemset(c->hcols2, 0, 8 * (m + 1) * (m + 4)));
   BK_CUDA(c, cudaMallocHost(&c->h_pinned, 2 * 8 * (m + 1) * (m + 4)));
   // number of partial-sum columns: one per CTA of the widest reduction grid
-  long long g = (n + 1 + 1023) / 1024 + 8;
+  long long g = (n + 2 + 255) / 256 + 8;  // worst case: one CTA per 256 values
   if (g < 4 * c->nsm) g = 4 * c->nsm;
   c->gmax = (int)g;
   BK_CUDA(c, cudaMalloc(&c->partials, 8 * (m + 4) * (size_t)c->gmax));
@@ -143,6 +148,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
     if (c->pc.dense[d]) cudaFree(c->pc.dense[d]);
   }
   if (c->counters) cudaFree(c->counters);
+  for (auto& kv : c->vec_live) cudaFree(kv.first);
   for (double* b : c->stage)
     if (b) cudaFree(b);
   for (double* b : c->tmp)
@@ -196,15 +202,28 @@ extern "C" int32_t bk_vec_alloc(bk_ctx* c, int64_t n, double** out) {
   BK_CHECK(c, n > 0, "bad length");
   BK_CUDA(c, cudaSetDevice(c->device));
   size_t len = ((size_t)n + 31) / 32 * 32;
+  // pooled: cudaMalloc/cudaFree synchronise the device and cost far more than a continuation-step kernel;
+  // freed vectors are recycled in stream order (every kernel of a context runs on its one stream)
+  for (size_t i = 0; i < c->vec_pool.size(); ++i) {
+    if (c->vec_pool[i].first == len) {
+      *out = c->vec_pool[i].second;
+      c->vec_pool[i] = c->vec_pool.back();
+      c->vec_pool.pop_back();
+      BK_CUDA(c, cudaMemsetAsync(*out, 0, 8 * len, c->stream));
+      return BK_OK;
+    }
+  }
   BK_CUDA(c, cudaMalloc(out, 8 * len));
+  c->vec_live[*out] = len;
   BK_CUDA(c, cudaMemsetAsync(*out, 0, 8 * len, c->stream));
   return BK_OK;
 }
 extern "C" int32_t bk_vec_free(bk_ctx* c, double* v) {
   if (!c) return BK_ERR_ARG;
   if (v) {
-    BK_CUDA(c, cudaStreamSynchronize(c->stream));
-    BK_CUDA(c, cudaFree(v));
+    auto it = c->vec_live.find(v);
+    BK_CHECK(c, it != c->vec_live.end(), "bk_vec_free: pointer was not allocated by bk_vec_alloc of this context");
+    c->vec_pool.push_back({it->second, v});
   }
   return BK_OK;
 }

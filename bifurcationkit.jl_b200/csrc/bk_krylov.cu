@@ -21,6 +21,7 @@
 #include <vector>
 #include "bk_common.cuh"
 #include "bk_stencil.cuh"
+#include "bk_krylov_tma.cuh"
 
 #define BK_DOT_UNROLL 4
 
@@ -224,6 +225,83 @@ static __global__ void __launch_bounds__(BK_THREADS) k_lincomb(double* __restric
     if (ok[e]) x[off[e]] = val[e];
 }
 
+
+// ------------------------------------------------------------------------------------------------ v2 (TMA ring) planning
+#define BK2_BLOCKS_PER_SM 4
+struct Plan2 {
+  int E, grid, NS, sred_off;
+  size_t smem;
+};
+// per-CTA dynamic shared memory budget that still lets BK2_BLOCKS_PER_SM CTAs share one SM (228 KB, 1 KB reserved per CTA)
+static inline size_t bk2_budget() { return (size_t)(233472 / BK2_BLOCKS_PER_SM) - 1024 - 512; }
+
+static Plan2 plan2(bk_ctx* c, long long units_of_256, size_t scratch_bytes_per_E(int), int force_E = 0) {
+  Plan2 p;
+  const long long slots = (long long)c->nsm * BK2_BLOCKS_PER_SM;
+  long long waves = (units_of_256 + slots * BK2_EMAX - 1) / (slots * BK2_EMAX);
+  if (waves < 1) waves = 1;
+  long long target = waves * slots;
+  long long E = (units_of_256 + target - 1) / target;
+  if (E < 1) E = 1;
+  if (E > BK2_EMAX) E = BK2_EMAX;
+  if (force_E) E = force_E;
+  p.E = (int)E;
+  p.grid = (int)((units_of_256 + E - 1) / E);
+  const size_t sred = sizeof(double) * 8 * (size_t)(c->m + 2);
+  const size_t stage = sizeof(double) * (size_t)E * BK2_ROW;
+  size_t budget = bk2_budget();
+  long long ns = budget > sred ? (long long)((budget - sred) / stage) : 2;
+  if (ns > BK2_MAXSTAGES) ns = BK2_MAXSTAGES;
+  if (ns < 2) ns = 2;
+  p.NS = (int)ns;
+  size_t ring = stage * (size_t)p.NS;
+  size_t scratch = scratch_bytes_per_E ? scratch_bytes_per_E(p.E) : 0;
+  size_t lo = ring > scratch ? ring : scratch;
+  lo = (lo + 127) / 128 * 128;
+  p.sred_off = (int)(lo / sizeof(double));
+  p.smem = lo + sred;
+  return p;
+}
+static size_t sh2_scratch_bytes(int E) { return sizeof(double) * (size_t)((BK2_ROW + 4) * (E + 4) + (BK2_ROW + 2) * (E + 2)); }
+
+#define BK2_DISPATCH(E, ...) \
+  switch (E) {                \
+    case 1: { constexpr int EE = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int EE = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int EE = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int EE = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int EE = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int EE = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int EE = 7; __VA_ARGS__; } break; \
+    default: { constexpr int EE = 8; __VA_ARGS__; } break; \
+  }
+
+template <typename K>
+static inline void bk2_ensure_smem(K kern, size_t bytes, size_t* cur) {
+  if (bytes > *cur) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    *cur = bytes;
+  }
+}
+
+static bool fused2_available(const OpDesc& op) { return op.kind == BK_SH2D && !op.bordered && (op.nx % 2 == 0); }
+
+static int launch_fused2(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* w, int j, double* hcol) {
+  const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
+  Plan2 p = plan2(c, (long long)tiles_x * op.ny, sh2_scratch_bytes);
+  p.grid = tiles_x * ((op.ny + p.E - 1) / p.E);
+  static size_t cur[BK2_EMAX + 1] = {0};
+  BK2_DISPATCH(p.E, {
+    bk2_ensure_smem(k2_fused<EE>, p.smem, &cur[EE]);
+    k2_fused<EE><<<p.grid, BK2_THREADS, p.smem, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
+                                                             c->counters + 0, hcol, c->gcoef, p.NS, p.sred_off);
+  });
+  c->stats.kernel_launches++;
+  BK_CUDA(c, cudaGetLastError());
+  return BK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static inline int chunk_grid(long long n) { return (int)((n + BK_TILE - 1) / BK_TILE); }
 
@@ -261,14 +339,14 @@ static int launch_fused(bk_ctx* c, const OpDesc& op, const double* in, const dou
 
 int bk_launch_dots(bk_ctx* c, const double* basis, const double* scales, const double* w, long long n, int j, double* hcol,
                    double* gcoef) {
-  size_t sm = dots_smem(j);
-  static size_t cur = 48 * 1024;
-  if (sm > cur) {
-    cudaFuncSetAttribute(k_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cur = sm;
-  }
-  k_dots<<<chunk_grid(n), BK_THREADS, sm, c->stream>>>(w, n, basis, c->ld, j, scales, c->partials, c->counters + 1, hcol,
-                                                       gcoef);
+  Plan2 p = plan2(c, (n + BK2_ROW - 1) / BK2_ROW, nullptr);
+  BK_CHECK(c, p.grid <= c->gmax, "partial-sum workspace too small");
+  static size_t cur[BK2_EMAX + 1] = {0};
+  BK2_DISPATCH(p.E, {
+    bk2_ensure_smem(k2_dots<EE>, p.smem, &cur[EE]);
+    k2_dots<EE><<<p.grid, BK2_THREADS, p.smem, c->stream>>>(w, n, basis, c->ld, j, scales, c->partials, c->counters + 1, hcol,
+                                                            gcoef, p.NS, p.sred_off);
+  });
   c->stats.kernel_launches++;
   BK_CUDA(c, cudaGetLastError());
   return BK_OK;
@@ -279,8 +357,14 @@ static int launch_dots(bk_ctx* c, const double* w, long long n, int j, double* h
 
 int bk_launch_update(bk_ctx* c, const double* basis, const double* gcoef, const double* w, long long n, int j, double* vout,
                      double* h_out, double* scale_out) {
-  k_update_norm<<<chunk_grid(n), BK_THREADS, 0, c->stream>>>(w, n, basis, c->ld, j, gcoef, vout, c->partials,
-                                                             c->counters + 2, h_out, scale_out);
+  Plan2 p = plan2(c, (n + BK2_ROW - 1) / BK2_ROW, nullptr);
+  BK_CHECK(c, p.grid <= c->gmax, "partial-sum workspace too small");
+  static size_t cur[BK2_EMAX + 1] = {0};
+  BK2_DISPATCH(p.E, {
+    bk2_ensure_smem(k2_update<EE>, p.smem, &cur[EE]);
+    k2_update<EE><<<p.grid, BK2_THREADS, p.smem, c->stream>>>(w, n, basis, c->ld, j, gcoef, vout, c->partials,
+                                                              c->counters + 2, h_out, scale_out, p.NS);
+  });
   c->stats.kernel_launches++;
   BK_CUDA(c, cudaGetLastError());
   return BK_OK;
@@ -340,7 +424,10 @@ static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lon
   const double* wfin = c->w;
   if (fuse) {
     ts.begin((*timer_slot)++);
-    BK_TRY(launch_fused(c, op, in, sp, c->w, j, hcol));
+    if (fused2_available(op))
+      BK_TRY(launch_fused2(c, op, in, sp, c->w, j, hcol));
+    else
+      BK_TRY(launch_fused(c, op, in, sp, c->w, j, hcol));
     ts.end();
   } else {
     BK_TRY(bk_launch_apply(c, op, in, sp, c->w));

@@ -1,0 +1,348 @@
+// bk_krylov_tma.cuh -- second-generation Arnoldi kernels: the Krylov basis is streamed through a
+// shared-memory ring by the TMA engine (cp.async.bulk + mbarrier), issued by a dedicated producer
+// warp, while 8 consumer warps do the fp64 FMAs.  One CTA owns a tile of up to 8 rows x 256 columns
+// (fused 2-D stencil) or a contiguous segment of up to 8 x 256 values (generic vectors); the tile
+// height E is chosen on the host so that the grid fills every SM of the B200 in whole, balanced waves
+// (the first version ran 512 CTAs on 444 resident slots: 1.15 waves, 24% of DRAM peak in ncu).
+//
+//   pass 1  k2_fused<E>  : w = a0 v + a1 J(u) v on a 256 x E tile (stencil from shared memory, halo 2),
+//                          then h_i = <v_i, w>, i < j, with V_i tiles arriving through the ring.
+//           k2_dots<E>   : same without the stencil (w read from memory).
+//   pass 2  k2_update<E> : v' = w - sum_i g_i V_i, ||v'||^2.
+// Reductions: warp shuffle -> per-CTA partial -> deterministic last-block sum (no atomics on data).
+#pragma once
+#include "bk_common.cuh"
+
+#define BK2_CONS 256
+#define BK2_THREADS 288
+#define BK2_EMAX 8
+#define BK2_ROW 256
+
+struct Tile2 {
+  long long base;  // offset of (row 0, col 0) inside a vector
+  int rs;          // row stride (elements)
+  int rows;        // valid rows (<= E)
+  int len;         // valid columns of rows 0..rows-2
+  int last_len;    // valid columns of the last row
+};
+
+__device__ __forceinline__ unsigned bk2_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk2_smem(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bk2_smem(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk2_smem(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BK2_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra BK2_DONE_%=;\n"
+      "bra BK2_WAIT_%=;\n"
+      "BK2_DONE_%=:\n"
+      "}\n" ::"r"(bk2_smem(b)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bk2_smem(dst)),
+               "l"(src), "r"(bytes), "r"(bk2_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+#define BK2_MAXSTAGES 8
+struct Ring {
+  unsigned long long full[BK2_MAXSTAGES];
+  unsigned long long empty[BK2_MAXSTAGES];
+};
+
+__device__ __forceinline__ void ring_init(Ring* rg, int NS) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&rg->full[s], 1);
+      mbar_init(&rg->empty[s], 8);
+    }
+    fence_mbar_init();
+  }
+}
+
+// Streams V_0..V_{j-1} restricted to the tile through the ring.  MODE 0: sred[i*8 + warp] = warp partial of
+// <V_i, val>; MODE 1: val -= g_i V_i.  Called by all BK2_THREADS threads after a __syncthreads().
+template <int E, int MODE>
+__device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __restrict__ V, long long ld, int j, double* ring,
+                                             int NS, Ring* rg, double (&val)[E], double* sred,
+                                             const double* __restrict__ gcoef) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 8) {
+    if (lane == 0) {
+      fence_proxy_async_smem();  // the ring may alias memory written through the generic proxy (stencil scratch)
+      const unsigned row_b = (unsigned)(((tl.len + 1) & ~1) * 8);
+      const unsigned last_b = (unsigned)(((tl.last_len + 1) & ~1) * 8);
+      const bool contiguous = (tl.rs == BK2_ROW) && (tl.len == BK2_ROW);
+      const unsigned total = row_b * (unsigned)(tl.rows - 1) + last_b;
+      for (int i = 0; i < j; ++i) {
+        const int s = i % NS, round = i / NS;
+        if (round > 0) mbar_wait(&rg->empty[s], (unsigned)((round - 1) & 1));
+        mbar_arrive_expect_tx(&rg->full[s], total);
+        const double* src = V + (long long)i * ld + tl.base;
+        double* dst = ring + (size_t)s * (E * BK2_ROW);
+        if (contiguous) {
+          bulk_g2s(dst, src, total, &rg->full[s]);
+        } else {
+          for (int r = 0; r < tl.rows - 1; ++r) bulk_g2s(dst + r * BK2_ROW, src + (long long)r * tl.rs, row_b, &rg->full[s]);
+          bulk_g2s(dst + (tl.rows - 1) * BK2_ROW, src + (long long)(tl.rows - 1) * tl.rs, last_b, &rg->full[s]);
+        }
+      }
+    }
+  } else {
+    const int t = threadIdx.x;
+    for (int i = 0; i < j; ++i) {
+      const int s = i % NS;
+      mbar_wait(&rg->full[s], (unsigned)((i / NS) & 1));
+      const double* st = ring + (size_t)s * (E * BK2_ROW) + t;
+      if (MODE == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
+          if (e < tl.rows && t < lim) a = fma(st[e * BK2_ROW], val[e], a);
+        }
+        a = bk_warp_sum(a);
+        if (lane == 0) sred[i * 8 + warp] = a;
+      } else {
+        const double g = __ldg(gcoef + i);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
+          if (e < tl.rows && t < lim) val[e] = fma(-g, st[e * BK2_ROW], val[e]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg->empty[s]);
+    }
+  }
+}
+
+// per-CTA partials of the j dot products + deterministic last-block reduction -> hcol[i] = s_i * sum, gcoef[i] = hcol[i] * s_i
+__device__ __forceinline__ void dots_finish(int j, const double* sred, const double* __restrict__ scales,
+                                            double* __restrict__ partials, unsigned int* counter, double* __restrict__ hcol,
+                                            double* __restrict__ gcoef, int* s_flag) {
+  const int G = gridDim.x;
+  for (int i = threadIdx.x; i < j; i += blockDim.x) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[i * 8 + k];
+    partials[(long long)i * G + blockIdx.x] = t;
+  }
+  if (bk_last_block(counter, s_flag)) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = warp; i < j; i += nw) {
+      double t = 0.0;
+      for (int k = lane; k < G; k += 32) t += __ldcg(partials + (long long)i * G + k);
+      t = bk_warp_sum(t);
+      if (lane == 0) {
+        const double s = scales[i];
+        const double h = s * t;
+        hcol[i] = h;
+        gcoef[i] = h * s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 2-D SH tile stencil
+// Tile = 256 columns x E rows at (x0, y0); thread t < 256 owns column x0 + t.  scratch: vs[(E+4)][260] | qs[(E+2)][258].
+template <int E>
+struct Sh2Scratch {
+  static constexpr int VX = BK2_ROW + 4, VY = E + 4, QX = BK2_ROW + 2, QY = E + 2;
+  static constexpr int V_ELEMS = VX * VY, Q_ELEMS = QX * QY;
+  static constexpr size_t BYTES = sizeof(double) * (size_t)(V_ELEMS + Q_ELEMS);
+};
+
+template <int E>
+__device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __restrict__ in, double in_scale, int x0, int y0,
+                                              double* scratch, double (&val)[E]) {
+  using S = Sh2Scratch<E>;
+  double* vs = scratch;
+  double* qs = scratch + S::V_ELEMS;
+  const int nx = op.nx, ny = op.ny;
+  for (int q = threadIdx.x; q < S::V_ELEMS; q += blockDim.x) {
+    int i = q % S::VX, jj = q / S::VX;
+    int gx = x0 - 2 + i, gy = y0 - 2 + jj;
+    gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
+    gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
+    vs[q] = in_scale * __ldg(in + gx + (long long)gy * nx);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < S::Q_ELEMS; q += blockDim.x) {
+    int i = q % S::QX, jj = q / S::QX;
+    int cx = x0 - 1 + i, cy = y0 - 1 + jj;
+    cx = (cx < 0 ? 0 : (cx > nx - 1 ? nx - 1 : cx)) - (x0 - 2);
+    cy = (cy < 0 ? 0 : (cy > ny - 1 ? ny - 1 : cy)) - (y0 - 2);
+    const double* p = vs + cx + cy * S::VX;
+    const double c0 = p[0];
+    qs[q] = c0 + op.cx * (p[-1] - 2.0 * c0 + p[1]) + op.cy * (p[-S::VX] - 2.0 * c0 + p[S::VX]);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const double l = op.par[0], nu = op.par[1];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int gx = x0 + t, gy = y0 + e;
+    double r = 0.0;
+    if (t < BK2_ROW && gx < nx && gy < ny) {
+      const double* p = qs + (t + 1) + (e + 1) * S::QX;
+      const double c0 = p[0];
+      const double l1v = c0 + op.cx * (p[-1] - 2.0 * c0 + p[1]) + op.cy * (p[-S::QX] - 2.0 * c0 + p[S::QX]);
+      const double v = vs[(t + 2) + (e + 2) * S::VX];
+      const double uu = __ldg(op.u + gx + (long long)gy * nx);
+      const double coef = l + uu * (2.0 * nu - 3.0 * uu);
+      r = op.a0 * v + op.a1 * (coef * v - l1v);
+    }
+    val[e] = r;
+  }
+}
+
+template <int E>
+static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, const double* __restrict__ in,
+                                                                  const double* __restrict__ in_scale_ptr,
+                                                                  double* __restrict__ w, const double* __restrict__ V,
+                                                                  long long ld, int j, const double* __restrict__ scales,
+                                                                  double* __restrict__ partials, unsigned int* counter,
+                                                                  double* __restrict__ hcol, double* __restrict__ gcoef,
+                                                                  int NS, int sred_off) {
+  extern __shared__ __align__(128) double smem2[];
+  __shared__ Ring rg;
+  __shared__ int s_flag;
+  double* ring = smem2;
+  double* sred = smem2 + sred_off;
+  ring_init(&rg, NS);
+  const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
+  const int x0 = (blockIdx.x % tiles_x) * BK2_ROW, y0 = (blockIdx.x / tiles_x) * E;
+  double val[E];
+  const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
+  sh2_tile_eval<E>(op, in, s, x0, y0, smem2, val);
+  Tile2 tl;
+  tl.base = x0 + (long long)y0 * op.nx;
+  tl.rs = op.nx;
+  tl.rows = min(E, op.ny - y0);
+  tl.len = min(BK2_ROW, op.nx - x0);
+  tl.last_len = tl.len;
+  if (threadIdx.x < tl.len) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < tl.rows) w[tl.base + (long long)e * tl.rs + threadIdx.x] = val[e];
+  }
+  fence_proxy_async_smem();  // generic-proxy accesses to the scratch are ordered before the TMA writes that reuse it
+  __syncthreads();           // scratch is dead, barriers are initialised: the ring takes over the shared memory
+  stream_basis<E, 0>(tl, V, ld, j, ring, NS, &rg, val, sred, nullptr);
+  __syncthreads();
+  dots_finish(j, sred, scales, partials, counter, hcol, gcoef, &s_flag);
+}
+
+__device__ __forceinline__ Tile2 linear_tile(long long n, int E) {
+  Tile2 tl;
+  tl.base = (long long)blockIdx.x * (E * BK2_ROW);
+  tl.rs = BK2_ROW;
+  long long rem = n - tl.base;
+  int rows = (int)((rem + BK2_ROW - 1) / BK2_ROW);
+  tl.rows = rows < E ? rows : E;
+  tl.len = BK2_ROW;
+  long long lastrem = rem - (long long)(tl.rows - 1) * BK2_ROW;
+  tl.last_len = lastrem < BK2_ROW ? (int)lastrem : BK2_ROW;
+  if (tl.rows == 1) tl.len = tl.last_len;
+  return tl;
+}
+
+template <int E>
+static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_dots(const double* __restrict__ w, long long n,
+                                                                 const double* __restrict__ V, long long ld, int j,
+                                                                 const double* __restrict__ scales,
+                                                                 double* __restrict__ partials, unsigned int* counter,
+                                                                 double* __restrict__ hcol, double* __restrict__ gcoef, int NS,
+                                                                 int sred_off) {
+  extern __shared__ __align__(128) double smem2[];
+  __shared__ Ring rg;
+  __shared__ int s_flag;
+  double* ring = smem2;
+  double* sred = smem2 + sred_off;
+  ring_init(&rg, NS);
+  const Tile2 tl = linear_tile(n, E);
+  double val[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
+    val[e] = (threadIdx.x < BK2_ROW && e < tl.rows && (int)threadIdx.x < lim) ? w[tl.base + e * BK2_ROW + threadIdx.x] : 0.0;
+  }
+  __syncthreads();
+  stream_basis<E, 0>(tl, V, ld, j, ring, NS, &rg, val, sred, nullptr);
+  __syncthreads();
+  dots_finish(j, sred, scales, partials, counter, hcol, gcoef, &s_flag);
+}
+
+template <int E>
+static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_update(const double* w, long long n,  // w may alias vout
+                                                                   const double* __restrict__ V, long long ld, int j,
+                                                                   const double* __restrict__ gcoef, double* vout,
+                                                                   double* __restrict__ partials, unsigned int* counter,
+                                                                   double* __restrict__ h_out, double* __restrict__ scale_out,
+                                                                   int NS) {
+  extern __shared__ __align__(128) double smem2[];
+  __shared__ Ring rg;
+  __shared__ double s_w[9];
+  __shared__ int s_flag;
+  double* ring = smem2;
+  ring_init(&rg, NS);
+  const Tile2 tl = linear_tile(n, E);
+  double val[E];
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
+    val[e] = (t < BK2_ROW && e < tl.rows && t < lim) ? w[tl.base + e * BK2_ROW + t] : 0.0;
+  }
+  __syncthreads();
+  stream_basis<E, 1>(tl, V, ld, j, ring, NS, &rg, val, nullptr, gcoef);
+  double acc = 0.0;
+  if (t < BK2_ROW) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
+      if (e < tl.rows && t < lim) {
+        vout[tl.base + e * BK2_ROW + t] = val[e];
+        acc = fma(val[e], val[e], acc);
+      }
+    }
+  }
+  acc = bk_warp_sum(acc);
+  const int lane = t & 31, wid = t >> 5;
+  if (lane == 0) s_w[wid] = acc;
+  __syncthreads();
+  if (t == 0) {
+    double r = 0;
+    for (int k = 0; k < 9; ++k) r += s_w[k];
+    partials[blockIdx.x] = r;
+  }
+  if (bk_last_block(counter, &s_flag)) {
+    double r = 0.0;
+    for (int k = t; k < (int)gridDim.x; k += blockDim.x) r += __ldcg(partials + k);
+    r = bk_warp_sum(r);
+    if (lane == 0) s_w[wid] = r;
+    __syncthreads();
+    if (t == 0) {
+      double q = 0;
+      for (int k = 0; k < 9; ++k) q += s_w[k];
+      const double h = sqrt(q);
+      *h_out = h;
+      *scale_out = 1.0 / h;
+    }
+  }
+}
