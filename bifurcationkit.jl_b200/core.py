@@ -93,7 +93,32 @@ class Context:
 
     def _like(self, x, n=None):
         n = len(x) if n is None else n
-        return DeviceVec(self, n) if isinstance(x, DeviceVec) else np.empty(n)
+        if isinstance(x, DeviceVec):
+            return DeviceVec(self, n)
+        return self.pinned_empty(n) if self.pin_host else np.empty(n)
+
+    # ---- pinned host arrays (option A callers): pooled cudaHostAlloc buffers exposed as NumPy arrays
+    pin_host = False
+
+    def pinned_empty(self, n):
+        import weakref
+        pool = self.__dict__.setdefault("_pin_pool", {})
+        free = pool.setdefault(n, [])
+        if free:
+            addr = free.pop()
+        else:
+            p = C.c_void_p()
+            _chk(self, self.lib.bk_host_alloc(self.handle, n, C.byref(p)))
+            addr = p.value
+        buf = (C.c_double * n).from_address(addr)
+        arr = np.frombuffer(buf, dtype=np.float64)
+        weakref.finalize(buf, free.append, addr)  # recycled when the last view dies; freed with the process
+        return arr
+
+    def pinned_array(self, a):
+        out = self.pinned_empty(len(a))
+        out[...] = a
+        return out
 
     # ---- K1 / K2 ----
     def residual(self, u, out=None):

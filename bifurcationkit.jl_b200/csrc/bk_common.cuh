@@ -36,7 +36,8 @@ struct Precond {
   double a0 = 0, a1 = 0;
   // DCT/DST tables (device)
   double2* tw[3] = {nullptr, nullptr, nullptr};     // FFT twiddles exp(-2 pi i k/n), k < n/2
-  double2* dtw[3] = {nullptr, nullptr, nullptr};    // DCT twiddles exp(-i pi k/(2n)), k < n
+  double2* dtw[3] = {nullptr, nullptr, nullptr};    // DCT twiddles exp(-i pi k/(2n)), k <= n/2
+  double2* wn[3] = {nullptr, nullptr, nullptr};     // real-FFT unpack twiddles exp(-2 pi i k/n), k <= n/2
   double* lam[3] = {nullptr, nullptr, nullptr};     // 1-D eigenvalues of the Laplacian factors
   double* dense[3] = {nullptr, nullptr, nullptr};   // dense transform matrices for non power-of-two sizes (n x n, forward)
   int pow2[3] = {0, 0, 0};

@@ -144,6 +144,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
   for (int d = 0; d < 3; ++d) {
     if (c->pc.tw[d]) cudaFree(c->pc.tw[d]);
     if (c->pc.dtw[d]) cudaFree(c->pc.dtw[d]);
+    if (c->pc.wn[d]) cudaFree(c->pc.wn[d]);
     if (c->pc.lam[d]) cudaFree(c->pc.lam[d]);
     if (c->pc.dense[d]) cudaFree(c->pc.dense[d]);
   }
@@ -224,6 +225,23 @@ extern "C" int32_t bk_vec_free(bk_ctx* c, double* v) {
     auto it = c->vec_live.find(v);
     BK_CHECK(c, it != c->vec_live.end(), "bk_vec_free: pointer was not allocated by bk_vec_alloc of this context");
     c->vec_pool.push_back({it->second, v});
+  }
+  return BK_OK;
+}
+// pinned host buffers for option-A callers (host-resident state): H2D/D2H at PCIe speed instead of the
+// pageable-memory staging path
+extern "C" int32_t bk_host_alloc(bk_ctx* c, int64_t n, double** out) {
+  if (!c || !out) return BK_ERR_ARG;
+  BK_CHECK(c, n > 0, "bad length");
+  BK_CUDA(c, cudaSetDevice(c->device));
+  BK_CUDA(c, cudaHostAlloc((void**)out, 8 * (size_t)n, cudaHostAllocDefault));
+  return BK_OK;
+}
+extern "C" int32_t bk_host_free(bk_ctx* c, double* p) {
+  if (!c) return BK_ERR_ARG;
+  if (p) {
+    BK_CUDA(c, cudaStreamSynchronize(c->stream));
+    BK_CUDA(c, cudaFreeHost(p));
   }
   return BK_OK;
 }

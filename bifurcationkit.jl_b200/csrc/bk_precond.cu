@@ -19,133 +19,7 @@
 #include <vector>
 #include "bk_common.cuh"
 
-struct LineGeom {
-  int n;         // line length
-  long long es;  // element stride along the line
-  int nx;        // extent of the contiguous (batch) index; 1 for x-lines
-  long long os;  // stride of the outer index
-  int nouter;    // number of outer indices
-};
-
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ int bitrev(int v, int logn) { return (int)(__brev((unsigned)v) >> (32 - logn)); }
-
-// In-place radix-2 DIT FFT on smem lines.  STRIDED: element e of line l at s[e*W + l]; else s[l*n + e].
-// inverse: conjugate twiddles (no 1/n scaling here).
-template <bool STRIDED>
-__device__ __forceinline__ void smem_fft(double2* s, int n, int logn, int W, const double2* __restrict__ tw, bool inverse) {
-  const int halfn = n >> 1;
-  for (int st = 0; st < logn; ++st) {
-    const int half = 1 << st;
-    const int tstep = halfn >> st;
-    for (int b = threadIdx.x; b < halfn * W; b += blockDim.x) {
-      int line, bf;
-      if (STRIDED) {
-        line = b % W;
-        bf = b / W;
-      } else {
-        line = b / halfn;
-        bf = b - line * halfn;
-      }
-      int grp = bf >> st, pos = bf & (half - 1);
-      int i0 = (grp << (st + 1)) + pos, i1 = i0 + half;
-      double2 t = __ldg(tw + pos * tstep);
-      if (inverse) t.y = -t.y;
-      double2* p0 = STRIDED ? s + (long long)i0 * W + line : s + (long long)line * n + i0;
-      double2* p1 = STRIDED ? s + (long long)i1 * W + line : s + (long long)line * n + i1;
-      double2 a = *p0, bb = cmul(t, *p1);
-      *p0 = make_double2(a.x + bb.x, a.y + bb.y);
-      *p1 = make_double2(a.x - bb.x, a.y - bb.y);
-    }
-    __syncthreads();
-  }
-}
-
-// DIR +1: forward DCT-II (unnormalised) of every line; DIR -1: its exact inverse.
-// SCALE (forward only used by the fused variant later): none here.
-template <bool STRIDED, int DIR>
-static __global__ void __launch_bounds__(256) k_dct_lines(const double* __restrict__ in, double* __restrict__ out, LineGeom g,
-                                                          int logn, int W, const double2* __restrict__ tw,
-                                                          const double2* __restrict__ dtw) {
-  extern __shared__ double2 sfft[];
-  const int n = g.n;
-  // which lines does this CTA own?
-  long long base;  // address of element 0 of line 0 of this CTA
-  int nl;          // number of valid lines
-  long long lstride;
-  if (STRIDED) {
-    int bx = blockIdx.x, o = blockIdx.y;
-    int x0 = bx * W;
-    nl = min(W, g.nx - x0);
-    base = x0 + (long long)o * g.os;
-    lstride = 1;
-  } else {
-    long long l0 = (long long)blockIdx.x * W;
-    nl = (int)min((long long)W, (long long)g.nouter - l0);
-    base = l0 * g.os;
-    lstride = g.os;
-  }
-  // load with Makhoul reordering + bit reversal
-  for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
-    int line, e;
-    if (STRIDED) {
-      line = q % W;
-      e = q / W;
-    } else {
-      line = q / n;
-      e = q - line * n;
-    }
-    double2 val = make_double2(0.0, 0.0);
-    int m;
-    if (DIR > 0) {
-      if (line < nl) val.x = in[base + line * lstride + (long long)e * g.es];
-      m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
-    } else {
-      // V[k] = conj(dtw[k]) * (C[k] - i C[n-k]),  C[n] = 0
-      if (line < nl) {
-        double ck = in[base + line * lstride + (long long)e * g.es];
-        double cnk = e > 0 ? in[base + line * lstride + (long long)(n - e) * g.es] : 0.0;
-        double2 t = __ldg(dtw + e);
-        t.y = -t.y;
-        val = cmul(t, make_double2(ck, -cnk));
-      }
-      m = e;
-    }
-    int p = bitrev(m, logn);
-    if (STRIDED)
-      sfft[(long long)p * W + line] = val;
-    else
-      sfft[(long long)line * n + p] = val;
-  }
-  __syncthreads();
-  smem_fft<STRIDED>(sfft, n, logn, W, tw, DIR < 0);
-  const double inv_n = 1.0 / n;
-  for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
-    int line, e;
-    if (STRIDED) {
-      line = q % W;
-      e = q / W;
-    } else {
-      line = q / n;
-      e = q - line * n;
-    }
-    if (line >= nl) continue;
-    double r;
-    if (DIR > 0) {
-      double2 v = STRIDED ? sfft[(long long)e * W + line] : sfft[(long long)line * n + e];
-      double2 t = __ldg(dtw + e);
-      r = t.x * v.x - t.y * v.y;  // Re(dtw * V)
-    } else {
-      // x[2m] = v[m], x[2m+1] = v[n-1-m]
-      int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
-      double2 v = STRIDED ? sfft[(long long)m * W + line] : sfft[(long long)line * n + m];
-      r = v.x * inv_n;
-    }
-    out[base + line * lstride + (long long)e * g.es] = r;
-  }
-}
+#include "bk_dct.cuh"
 
 // dense transform of every line: out[line, k] = sum_e M[k*n + e] in[line, e]
 static __global__ void __launch_bounds__(256) k_dense_lines(const double* __restrict__ in, double* __restrict__ out, LineGeom g,
@@ -202,7 +76,7 @@ static __global__ void k_thomas(const double* __restrict__ tri, const double* __
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static bool is_pow2(long long n) { return n >= 8 && n <= 4096 && (n & (n - 1)) == 0; }
+static bool is_pow2(long long n) { return n >= 16 && n <= 4096 && (n & (n - 1)) == 0; }
 static int ilog2(long long n) {
   int l = 0;
   while ((1LL << l) < n) ++l;
@@ -231,11 +105,16 @@ static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type) {
   BK_TRY(upload(c, (void**)&pc.lam[d], lam.data(), 8 * n));
   pc.pow2[d] = (type == 0 && is_pow2(n)) ? 1 : 0;
   if (pc.pow2[d]) {
-    std::vector<double2> tw(n / 2), dtw(n);
-    for (long long k = 0; k < n / 2; ++k) tw[k] = make_double2((double)cosl(-2.0L * PI * k / n), (double)sinl(-2.0L * PI * k / n));
-    for (long long k = 0; k < n; ++k) dtw[k] = make_double2((double)cosl(-PI * k / (2.0L * n)), (double)sinl(-PI * k / (2.0L * n)));
-    BK_TRY(upload(c, (void**)&pc.tw[d], tw.data(), 16 * (n / 2)));
-    BK_TRY(upload(c, (void**)&pc.dtw[d], dtw.data(), 16 * n));
+    const long long M = n / 2;
+    std::vector<double2> tw(M / 2), wn(M + 1), dtw(M + 1);
+    for (long long k = 0; k < M / 2; ++k) tw[k] = make_double2((double)cosl(-2.0L * PI * k / M), (double)sinl(-2.0L * PI * k / M));
+    for (long long k = 0; k <= M; ++k) {
+      wn[k] = make_double2((double)cosl(-2.0L * PI * k / n), (double)sinl(-2.0L * PI * k / n));
+      dtw[k] = make_double2((double)cosl(-PI * k / (2.0L * n)), (double)sinl(-PI * k / (2.0L * n)));
+    }
+    BK_TRY(upload(c, (void**)&pc.tw[d], tw.data(), 16 * (M / 2)));
+    BK_TRY(upload(c, (void**)&pc.wn[d], wn.data(), 16 * (M + 1)));
+    BK_TRY(upload(c, (void**)&pc.dtw[d], dtw.data(), 16 * (M + 1)));
   } else {
     // dense forward F (n x n) followed by dense inverse Finv (n x n)
     std::vector<double> M(2 * n * n);
@@ -311,7 +190,8 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
 }
 
 // one 1-D transform pass along dimension d over `nblocks` consecutive blocks of nx*ny(*nz) values
-static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* out, int nx, int ny, int nz) {
+static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* out, int nx, int ny, int nz,
+                          const SymbolArgs* fused_sym = nullptr) {
   Precond& pc = c->pc;
   LineGeom g;
   const int dims[3] = {nx, ny, nz};
@@ -336,18 +216,36 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     int W = 4096 / g.n;
     if (W < 1) W = 1;
     if (W > 16) W = 16;
-    size_t sm = sizeof(double2) * (size_t)g.n * W;
-    int logn = ilog2(g.n);
+    const int mode = fused_sym ? 2 : (dir > 0 ? 0 : 1);
+    size_t sm = sizeof(double2) * (size_t)(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
+    int logM = ilog2(g.n / 2);
+    DctTables tb{pc.tw[d], pc.wn[d], pc.dtw[d]};
+    SymbolArgs sy{nullptr, nullptr, nullptr, 0.0};
+    if (fused_sym) sy = *fused_sym;
+    static bool attr = false;
+    if (!attr) {
+      const int mx = 160 * 1024;
+      cudaFuncSetAttribute(k_dct2<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaFuncSetAttribute(k_dct2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaFuncSetAttribute(k_dct2<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaFuncSetAttribute(k_dct2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaFuncSetAttribute(k_dct2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      attr = true;
+    }
     if (d == 0) {
-      auto kern = dir > 0 ? k_dct_lines<false, 1> : k_dct_lines<false, -1>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       int grid = (g.nouter + W - 1) / W;
-      kern<<<grid, 256, sm, c->stream>>>(in, out, g, logn, W, pc.tw[d], pc.dtw[d]);
+      if (mode == 0)
+        k_dct2<false, 0><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+      else
+        k_dct2<false, 1><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
     } else {
-      auto kern = dir > 0 ? k_dct_lines<true, 1> : k_dct_lines<true, -1>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       dim3 grid((g.nx + W - 1) / W, g.nouter);
-      kern<<<grid, 256, sm, c->stream>>>(in, out, g, logn, W, pc.tw[d], pc.dtw[d]);
+      if (mode == 0)
+        k_dct2<true, 0><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+      else if (mode == 1)
+        k_dct2<true, 1><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+      else
+        k_dct2<true, 2><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
     }
   } else {
     const double* M = pc.dense[d] + (dir > 0 ? 0 : (size_t)g.n * g.n);
@@ -375,25 +273,41 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
     const int nd = c->kind == BK_SH3D ? 3 : 2;
     double* A = pc.work;
     double* B = pc.work2;
-    BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
-    BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
-    double* cur = B;
-    double* oth = A;
-    if (nd == 3) {
-      BK_TRY(transform_pass(c, 2, +1, B, A, nx, ny, nz));
-      cur = A;
-      oth = B;
+    const int last = nd - 1;
+    if (pc.pow2[last]) {
+      // x fwd, [y fwd,] (last dim: fwd + symbol + inverse in one kernel), [y inv,] x inv
+      SymbolArgs sy{pc.lam[last], pc.lam[0], nd == 3 ? pc.lam[1] : nullptr, pc.a0};
+      BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
+      if (nd == 3) {
+        BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
+        BK_TRY(transform_pass(c, 2, +1, B, A, nx, ny, nz, &sy));
+        BK_TRY(transform_pass(c, 1, -1, A, B, nx, ny, nz));
+        BK_TRY(transform_pass(c, 0, -1, B, out, nx, ny, nz));
+      } else {
+        BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz, &sy));
+        BK_TRY(transform_pass(c, 0, -1, B, out, nx, ny, nz));
+      }
+    } else {
+      BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
+      BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
+      double* cur = B;
+      double* oth = A;
+      if (nd == 3) {
+        BK_TRY(transform_pass(c, 2, +1, B, A, nx, ny, nz));
+        cur = A;
+        oth = B;
+      }
+      k_sh_symbol_div<<<lin_grid(c, N), 256, 0, c->stream>>>(cur, nx, ny, nz, pc.lam[0], pc.lam[1],
+                                                            nd == 3 ? pc.lam[2] : nullptr, pc.a0);
+      c->stats.kernel_launches++;
+      BK_CUDA(c, cudaGetLastError());
+      if (nd == 3) {
+        BK_TRY(transform_pass(c, 2, -1, cur, oth, nx, ny, nz));
+        std::swap(cur, oth);
+      }
+      BK_TRY(transform_pass(c, 1, -1, cur, oth, nx, ny, nz));
+      BK_TRY(transform_pass(c, 0, -1, oth, out, nx, ny, nz));
     }
-    k_sh_symbol_div<<<lin_grid(c, N), 256, 0, c->stream>>>(cur, nx, ny, nz, pc.lam[0], pc.lam[1], nd == 3 ? pc.lam[2] : nullptr,
-                                                          pc.a0);
-    c->stats.kernel_launches++;
-    BK_CUDA(c, cudaGetLastError());
-    if (nd == 3) {
-      BK_TRY(transform_pass(c, 2, -1, cur, oth, nx, ny, nz));
-      std::swap(cur, oth);
-    }
-    BK_TRY(transform_pass(c, 1, -1, cur, oth, nx, ny, nz));
-    BK_TRY(transform_pass(c, 0, -1, oth, out, nx, ny, nz));
   } else if (pc.kind == BK_PC_CGL_DST) {
     const int nx = (int)c->dims[0], ny = (int)c->dims[1];
     const long long nblk = (c->kind == BK_POTRAP_CGL2D) ? 2 * c->dims[2] : 2;  // components x slices

@@ -20,7 +20,7 @@ BK_ORTH_CGS, BK_ORTH_CGS2 = 0, 1
 SYMBOLS = [
     "bk_ctx_create", "bk_ctx_destroy", "bk_last_error", "bk_problem_size", "bk_set_params", "bk_get_stats",
     "bk_set_timing", "bk_sync", "bk_stream",
-    "bk_vec_alloc", "bk_vec_free", "bk_vec_upload", "bk_vec_download", "bk_vec_copy", "bk_vec_zero", "bk_vec_scale",
+    "bk_vec_alloc", "bk_vec_free", "bk_host_alloc", "bk_host_free", "bk_vec_upload", "bk_vec_download", "bk_vec_copy", "bk_vec_zero", "bk_vec_scale",
     "bk_vec_axpby", "bk_vec_dot", "bk_vec_norm2", "bk_vec_norminf", "bk_vec_diffdot",
     "bk_residual", "bk_jac_set_state", "bk_jvp", "bk_precond_setup", "bk_precond_apply",
     "bk_gmres", "bk_gmres2", "bk_bls_bordering", "bk_bls_matrixfree", "bk_bls_map",
@@ -78,6 +78,8 @@ def load():
         "bk_stream": [C.c_void_p],
         "bk_vec_alloc": [C.c_void_p, i64, C.POINTER(C.c_void_p)],
         "bk_vec_free": [C.c_void_p, vp],
+        "bk_host_alloc": [C.c_void_p, i64, C.POINTER(C.c_void_p)],
+        "bk_host_free": [C.c_void_p, vp],
         "bk_vec_upload": [C.c_void_p, vp, vp, i64],
         "bk_vec_download": [C.c_void_p, vp, vp, i64],
         "bk_vec_copy": [C.c_void_p, vp, vp, i64],

@@ -21,10 +21,15 @@ SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # src/Problems.jl:69
 
 class V:
     """VectorInterface subset (src/BorderedArrays.jl:86-217) for DeviceVec and ndarray."""
+    host_alloc = None  # optional n -> ndarray factory (e.g. Context.pinned_empty) for host-resident state
 
     @staticmethod
     def copy(x):
-        return x.copy()
+        if isinstance(x, DeviceVec) or V.host_alloc is None:
+            return x.copy()
+        y = V.host_alloc(len(x))
+        y[...] = x
+        return y
 
     @staticmethod
     def copyto(dst, src):
@@ -69,7 +74,13 @@ class V:
 
     @staticmethod
     def zeros_like(x):
-        return x.copy().zero_() if isinstance(x, DeviceVec) else np.zeros_like(x)
+        if isinstance(x, DeviceVec):
+            return x.copy().zero_()
+        if V.host_alloc is None:
+            return np.zeros_like(x)
+        y = V.host_alloc(len(x))
+        y[...] = 0.0
+        return y
 
 
 norminf = V.norminf

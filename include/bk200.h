@@ -91,6 +91,9 @@ void*   bk_stream(bk_ctx* ctx);                              /* cudaStream_t the
 /* ---- S11 device vectors: BorderedArray / VectorInterface algebra (src/BorderedArrays.jl:30-35,53-70,79-217) */
 int32_t bk_vec_alloc(bk_ctx* ctx, int64_t n, double** out);
 int32_t bk_vec_free(bk_ctx* ctx, double* v);
+/* pinned (page-locked) host buffers for callers that keep the state on the host (option A) */
+int32_t bk_host_alloc(bk_ctx* ctx, int64_t n, double** out);
+int32_t bk_host_free(bk_ctx* ctx, double* p);
 int32_t bk_vec_upload(bk_ctx* ctx, double* dst_dev, const double* src_host, int64_t n);
 int32_t bk_vec_download(bk_ctx* ctx, double* dst_host, const double* src_dev, int64_t n);
 int32_t bk_vec_copy(bk_ctx* ctx, double* dst, const double* src, int64_t n);          /* _copyto! */
