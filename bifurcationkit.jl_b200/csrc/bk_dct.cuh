@@ -38,6 +38,10 @@ __device__ __forceinline__ double2 dct_cmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 dct_conj(double2 a) { return make_double2(a.x, -a.y); }
 __device__ __forceinline__ int dct_bitrev(int v, int logm) { return (int)(__brev((unsigned)v) >> (32 - logm)); }
+// shared-memory index padding: one extra complex slot per 8 (power-of-two strides would otherwise map the
+// radix-4 butterflies of the early passes onto the same banks: 16-way conflicts measured as ~20 us kernels)
+__device__ __forceinline__ int dct_pad(int i) { return i + (i >> 3); }
+#define DCT_PADDED(M) ((M) + ((M) >> 3) + 1)
 
 // in-place DIT FFT of W lines of M complex points held bit-reversed in shared memory
 template <bool STRIDED>
@@ -47,8 +51,9 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, cons
     for (int b = threadIdx.x; b < (M >> 1) * W; b += blockDim.x) {
       int line = STRIDED ? b % W : b / (M >> 1);
       int bf = STRIDED ? b / W : b - line * (M >> 1);
-      double2* p0 = STRIDED ? s + (long long)(2 * bf) * W + line : s + (long long)line * M + 2 * bf;
-      double2* p1 = STRIDED ? p0 + W : p0 + 1;
+      const int MP = DCT_PADDED(M);
+      double2* p0 = STRIDED ? s + (long long)dct_pad(2 * bf) * W + line : s + (long long)line * MP + dct_pad(2 * bf);
+      double2* p1 = STRIDED ? s + (long long)dct_pad(2 * bf + 1) * W + line : s + (long long)line * MP + dct_pad(2 * bf + 1);
       double2 a = *p0, c = *p1;
       *p0 = make_double2(a.x + c.x, a.y + c.y);
       *p1 = make_double2(a.x - c.x, a.y - c.y);
@@ -70,19 +75,22 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, cons
         w2.y = -w2.y;
       }
       const double2 w3 = inverse ? make_double2(-w2.y, w2.x) : make_double2(w2.y, -w2.x);  // w2 * (+-i)
-      const long long str = STRIDED ? (long long)half * W : half;
-      double2* p = STRIDED ? s + (long long)i * W + line : s + (long long)line * M + i;
-      double2 a = p[0], b = p[str], c = p[2 * str], d = p[3 * str];
+      const int MP = DCT_PADDED(M);
+      double2* pa = STRIDED ? s + (long long)dct_pad(i) * W + line : s + (long long)line * MP + dct_pad(i);
+      double2* pb = STRIDED ? s + (long long)dct_pad(i + half) * W + line : s + (long long)line * MP + dct_pad(i + half);
+      double2* pc = STRIDED ? s + (long long)dct_pad(i + 2 * half) * W + line : s + (long long)line * MP + dct_pad(i + 2 * half);
+      double2* pd = STRIDED ? s + (long long)dct_pad(i + 3 * half) * W + line : s + (long long)line * MP + dct_pad(i + 3 * half);
+      double2 a = *pa, b = *pb, c = *pc, d = *pd;
       double2 t = dct_cmul(w1, b);
       double2 a1 = make_double2(a.x + t.x, a.y + t.y), b1 = make_double2(a.x - t.x, a.y - t.y);
       t = dct_cmul(w1, d);
       double2 c1 = make_double2(c.x + t.x, c.y + t.y), d1 = make_double2(c.x - t.x, c.y - t.y);
       t = dct_cmul(w2, c1);
-      p[0] = make_double2(a1.x + t.x, a1.y + t.y);
-      p[2 * str] = make_double2(a1.x - t.x, a1.y - t.y);
+      *pa = make_double2(a1.x + t.x, a1.y + t.y);
+      *pc = make_double2(a1.x - t.x, a1.y - t.y);
       t = dct_cmul(w3, d1);
-      p[str] = make_double2(b1.x + t.x, b1.y + t.y);
-      p[3 * str] = make_double2(b1.x - t.x, b1.y - t.y);
+      *pb = make_double2(b1.x + t.x, b1.y + t.y);
+      *pd = make_double2(b1.x - t.x, b1.y - t.y);
     }
     __syncthreads();
   }
@@ -90,13 +98,14 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, cons
 
 // shared memory: s[M*W] complex, and for MODE 2 additionally cb[n*W] real
 template <bool STRIDED, int MODE>
-static __global__ void __launch_bounds__(256) k_dct2(const double* __restrict__ in, double* __restrict__ out, LineGeom g, int logM,
+static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__ in, double* __restrict__ out, LineGeom g, int logM,
                                                       int W, DctTables tb, SymbolArgs sy) {
   extern __shared__ __align__(16) double2 sdct[];
   const int n = g.n, M = n >> 1;
   double2* s = sdct;
   double* sd = reinterpret_cast<double*>(sdct);
-  double* cb = reinterpret_cast<double*>(sdct + (size_t)M * W);
+  const int MP = DCT_PADDED(M);
+  double* cb = reinterpret_cast<double*>(sdct + (size_t)MP * W);
   long long base, lstride;
   int nl, x0 = 0, o = 0;
   if (STRIDED) {
@@ -121,7 +130,7 @@ static __global__ void __launch_bounds__(256) k_dct2(const double* __restrict__ 
       double xv = (line < nl) ? in[base + line * lstride + (long long)e * g.es] : 0.0;
       int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
       int p = dct_bitrev(m >> 1, logM);
-      long long ci = STRIDED ? (long long)p * W + line : (long long)line * M + p;
+      long long ci = STRIDED ? (long long)dct_pad(p) * W + line : (long long)line * MP + dct_pad(p);
       sd[2 * ci + (m & 1)] = xv;
     }
     __syncthreads();
@@ -131,8 +140,8 @@ static __global__ void __launch_bounds__(256) k_dct2(const double* __restrict__ 
       int k = STRIDED ? q / W : q - line * (M + 1);
       if (line >= nl) continue;
       int k0 = k & (M - 1), k1 = (M - k) & (M - 1);
-      double2 zk = STRIDED ? s[(long long)k0 * W + line] : s[(long long)line * M + k0];
-      double2 zc = dct_conj(STRIDED ? s[(long long)k1 * W + line] : s[(long long)line * M + k1]);
+      double2 zk = STRIDED ? s[(long long)dct_pad(k0) * W + line] : s[(long long)line * MP + dct_pad(k0)];
+      double2 zc = dct_conj(STRIDED ? s[(long long)dct_pad(k1) * W + line] : s[(long long)line * MP + dct_pad(k1)]);
       double2 ev = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y + zc.y));
       double2 df = make_double2(zk.x - zc.x, zk.y - zc.y);
       double2 od = make_double2(0.5 * df.y, -0.5 * df.x);  // -i (zk - zc) / 2
@@ -188,9 +197,9 @@ static __global__ void __launch_bounds__(256) k_dct2(const double* __restrict__ 
       }
       int p = dct_bitrev(k, logM);
       if (STRIDED)
-        s[(long long)p * W + line] = z;
+        s[(long long)dct_pad(p) * W + line] = z;
       else
-        s[(long long)line * M + p] = z;
+        s[(long long)line * MP + dct_pad(p)] = z;
     }
     __syncthreads();
     dct_fft<STRIDED>(s, M, logM, W, tb.tw, true);
@@ -199,7 +208,7 @@ static __global__ void __launch_bounds__(256) k_dct2(const double* __restrict__ 
       int e = STRIDED ? q / W : q - line * n;
       if (line >= nl) continue;
       int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
-      long long ci = STRIDED ? (long long)(m >> 1) * W + line : (long long)line * M + (m >> 1);
+      long long ci = STRIDED ? (long long)dct_pad(m >> 1) * W + line : (long long)line * MP + dct_pad(m >> 1);
       out[base + line * lstride + (long long)e * g.es] = sd[2 * ci + (m & 1)] * inv_m;
     }
   }

@@ -55,6 +55,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(bk2_smem(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -229,13 +232,20 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
   const int x0 = (blockIdx.x % tiles_x) * BK2_ROW, y0 = (blockIdx.x / tiles_x) * E;
   double val[E];
   const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
-  sh2_tile_eval<E>(op, in, s, x0, y0, smem2, val);
   Tile2 tl;
   tl.base = x0 + (long long)y0 * op.nx;
   tl.rs = op.nx;
   tl.rows = min(E, op.ny - y0);
   tl.len = min(BK2_ROW, op.nx - x0);
   tl.last_len = tl.len;
+  if (threadIdx.x == BK2_CONS) {
+    // the ring cannot start before the stencil scratch is dead: pull the first basis tiles into L2 meanwhile
+    const unsigned row_b = (unsigned)(((tl.len + 1) & ~1) * 8);
+    const int npf = j < 2 * NS ? j : 2 * NS;
+    for (int i = 0; i < npf; ++i)
+      for (int r = 0; r < tl.rows; ++r) bulk_prefetch_l2(V + (long long)i * ld + tl.base + (long long)r * tl.rs, row_b);
+  }
+  sh2_tile_eval<E>(op, in, s, x0, y0, smem2, val);
   if (threadIdx.x < tl.len) {
 #pragma unroll
     for (int e = 0; e < E; ++e)

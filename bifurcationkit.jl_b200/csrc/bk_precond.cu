@@ -15,6 +15,7 @@
 //   examples/cGL2d.jl:209-213); for potrap contexts it is applied slice by slice (block Jacobi, cf.
 //   jacobian_block_diag, src/periodicorbit/PeriodicOrbitTrapeze.jl:619-643).
 #include <cmath>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 #include "bk_common.cuh"
@@ -213,11 +214,20 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     g.nouter = ny;
   }
   if (pc.pow2[d]) {
+    static int env_w = -1, env_t = -1;
+    if (env_w < 0) {
+      const char* a = getenv("BK_DCT_W");
+      const char* b = getenv("BK_DCT_THREADS");
+      env_w = a ? atoi(a) : 0;
+      env_t = b ? atoi(b) : 0;
+    }
     int W = 4096 / g.n;
     if (W < 1) W = 1;
     if (W > 16) W = 16;
+    if (env_w > 0) W = env_w;
+    const int nthr = env_t > 0 ? env_t : 512;
     const int mode = fused_sym ? 2 : (dir > 0 ? 0 : 1);
-    size_t sm = sizeof(double2) * (size_t)(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
+    size_t sm = sizeof(double2) * (size_t)DCT_PADDED(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
     int logM = ilog2(g.n / 2);
     DctTables tb{pc.tw[d], pc.wn[d], pc.dtw[d]};
     SymbolArgs sy{nullptr, nullptr, nullptr, 0.0};
@@ -235,17 +245,17 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     if (d == 0) {
       int grid = (g.nouter + W - 1) / W;
       if (mode == 0)
-        k_dct2<false, 0><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<false, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
       else
-        k_dct2<false, 1><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<false, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
     } else {
       dim3 grid((g.nx + W - 1) / W, g.nouter);
       if (mode == 0)
-        k_dct2<true, 0><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<true, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
       else if (mode == 1)
-        k_dct2<true, 1><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<true, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
       else
-        k_dct2<true, 2><<<grid, 256, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<true, 2><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
     }
   } else {
     const double* M = pc.dense[d] + (dir > 0 ? 0 : (size_t)g.n * g.n);
