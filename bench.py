@@ -260,22 +260,14 @@ def main():
     if world > 1:
         t0 = time.perf_counter()
         P = bk.palc
-        seeds = {}
         stride = args.steps + args.warmup
-
-        def grab(st):
-            if st.step % stride == 0 or (st.step - 1) % stride == 0:
-                seeds[st.step] = (st.z_u.copy(), st.z_p)
-            return st.step < rank * stride + 1
-
-        cp = P.ContinuationPar(max_steps=stride * (world - 1) + 1,
-                               newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls), **CONT)
-        prob = P.BifurcationProblemB200(ctx, u_front, PAR, lens=0)
         if rank > 0:
+            grab = bk.segments.SeedGrabber(rank, stride, lambda v: v.copy())
+            cp = P.ContinuationPar(max_steps=stride * rank + 1,
+                                   newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls), **CONT)
+            prob = P.BifurcationProblemB200(ctx, u_front, PAR, lens=0)
             P.continuation(prob, P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False)), cp, normC=P.norminf, callback=grab)
-            a, b = rank * stride, rank * stride + 1
-            u_start, p_start = seeds[a]
-            u1, p1 = seeds[b]
+            u_start, p_start, u1, p1 = grab.pair()
         ctx.sync()
         scout_ms = (time.perf_counter() - t0) * 1e3
 
@@ -299,12 +291,8 @@ def main():
         tmax = max(float(t[0]) for t in allt)
         total_steps = int(sum(float(t[1]) for t in allt))
         # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear) per batch
-        R = torch.zeros((args.steps + args.warmup + 1, 4), dtype=torch.float64, device=f"cuda:{dev}")
-        for i, r in enumerate(rows[: R.shape[0]]):
-            R[i] = torch.tensor([r["param"], r["x"], r["itnewton"], r["itlinear"]], dtype=torch.float64)
-        allR = [torch.zeros_like(R) for _ in range(world)]
-        dist.all_gather(allR, R)
-        branch = torch.cat(allR).cpu().numpy()
+        gathered = bk.segments.all_gather_rows(rows, args.steps + args.warmup + 1, dist, torch, f"cuda:{dev}")
+        branch = bk.segments.merge_branch(gathered)
     else:
         tmax, total_steps = my_ms, nsteps
         branch = np.array([[r["param"], r["x"], r["itnewton"], r["itlinear"]] for r in rows])
@@ -331,6 +319,7 @@ def main():
            "warmup": args.warmup, "ms_per_step": tmax / max(1, nsteps), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "grid": [n, n], "mean_itnewton": itn, "mean_itlinear_per_step": itl,
+                      "rejected_steps": int(st.nfail), "corrector_work": {"newton_its": int(st.work_newton), "linear_its": int(st.work_linear)},
                       "l2": "256 MiB L2 flush between timed steps (outside the event pairs); Krylov basis per solve > L2",
                       "parallelism": f"branch segments x{world}, replicated state" if world > 1 else "1 GPU",
                       "scout_ms": scout_ms, "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())]},

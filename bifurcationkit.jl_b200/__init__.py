@@ -12,3 +12,4 @@ from .lib import (BK200Error, BK_CHAN, BK_SH2D, BK_SH3D, BK_CGL2D, BK_POTRAP_CGL
 from .core import (Context, DeviceVec, Jacobian, GMRESB200, BorderingBLSB200, MatrixFreeBLSB200, ShiftInvertB200,
                    bls_map, make_opts, hessenberg_eig)
 from . import palc
+from . import segments

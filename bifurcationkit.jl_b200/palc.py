@@ -247,6 +247,9 @@ class ContState:
     stop: bool = False
     n_unstable: tuple = (-1, -1)
     eigvals: object = None
+    nfail: int = 0
+    work_newton: int = 0
+    work_linear: int = 0
 
 
 def _secant(st, theta):
@@ -348,6 +351,9 @@ def continuation(prob, alg, contpar, normC=V.norm2, u1=None, p1=None, verbose=Fa
             sol = newton_palc(prob, st.z_u, st.z_p, st.tau_u, st.tau_p, st.zpred_u, st.zpred_p, st.ds, theta, contpar,
                               bls, normC)
         st.converged, st.itnewton, st.itlinear = sol.converged, sol.itnewton, sol.itlineartot
+        st.work_newton += sol.itnewton      # all corrector work, including rejected attempts
+        st.work_linear += sol.itlineartot
+        st.nfail += 0 if sol.converged else 1
         if sol.converged:
             st.zold_u, st.z_u = st.z_u, st.zold_u  # swap buffers: z_old <- z
             st.zold_p = st.z_p
