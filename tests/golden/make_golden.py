@@ -23,7 +23,7 @@ def main():
     u = problems.sh2d_sol0(*dims, LX, LY)
     v = rng.standard_normal(sh.N)
     out.update(sh2d_u=u, sh2d_v=v, sh2d_F=sh.F(u), sh2d_Jv=sh.dF(u, v), sh2d_Pinv_v=precond.dct_precond(dims, (LX, LY), 1.0)(v))
-    x, ok, it = krylov.GMRESIterativeSolvers(reltol=1e-10, restart=80, maxiter=80)(lambda w: sh.dF(u, w), v, a0=3.0, a1=-1.0)
+    x, ok, it = krylov.GMRESIterativeSolvers(reltol=1e-10, restart=80, maxiter=80)(lambda w: sh.dF(u, w), v, a0=30.0, a1=-1.0)
     out.update(sh2d_gmres_x=x, sh2d_gmres_iters=np.array([it]))
     # P3: SH3d 12 x 10 x 8
     d3, L3 = (12, 10, 8), (2 * np.pi, 2 * np.pi, 1.5 * np.pi)

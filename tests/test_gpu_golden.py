@@ -23,7 +23,7 @@ def test_kernels_vs_golden():
     assert _rel(J(G["sh2d_v"]), G["sh2d_Jv"]) < 1e-12
     c.precond_setup(bk.BK_PC_SH_DCT, 1.0)
     assert _rel(c.precond_apply(G["sh2d_v"]), G["sh2d_Pinv_v"]) < 1e-11
-    x, ok, it = bk.GMRESB200(reltol=1e-10, restart=80, maxiter=80)(J, G["sh2d_v"], a0=3.0, a1=-1.0)
+    x, ok, it = bk.GMRESB200(reltol=1e-10, restart=80, maxiter=80)(J, G["sh2d_v"], a0=30.0, a1=-1.0)
     assert ok and abs(it - int(G["sh2d_gmres_iters"][0])) <= 2 and _rel(x, G["sh2d_gmres_x"]) < 1e-8
     c3 = bk.Context(bk.BK_SH3D, (12, 10, 8), (2 * np.pi, 2 * np.pi, 1.5 * np.pi), krylov_m=4, params=(0.1, 1.2))
     assert _rel(c3.residual(G["sh3d_u"]), G["sh3d_F"]) < 1e-12 and _rel(c3.jacobian(G["sh3d_u"])(G["sh3d_v"]), G["sh3d_Jv"]) < 1e-12
