@@ -43,6 +43,7 @@ def domain(n):
 PAR = (-0.1, 1.3)                            # (l, nu) examples/SH2d-fronts.jl:55
 CONT = dict(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0)  # examples/SH2d-fronts.jl:86
 GMRES = dict(reltol=1e-5, restart=100, maxiter=100)  # examples/SH2d-fronts.jl:122 (reltol), config "GMRES(100)"
+BLS = {"kind": "matrixfree"}  # MatrixFreeBLS (1 GMRES on the N+1 bordered system) or "bordering" (BorderingBLS: 2 GMRES + BEC)
 
 
 def sol0(n):
@@ -129,7 +130,7 @@ def gpu_run(bk, ctx, ls, u_start, p_start, steps, warmup, torch, timing=True, u1
     P = bk.palc
     cp = P.ContinuationPar(max_steps=warmup + steps, newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls),
                            **CONT)
-    alg = P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False))
+    alg = P.PALC(bls=bk.MatrixFreeBLSB200(ls) if BLS["kind"] == "matrixfree" else bk.BorderingBLSB200(ls, check_precision=False))
     pars = list(PAR)
     pars[0] = p_start
     prob = P.BifurcationProblemB200(ctx, u_start, pars, lens=0)
@@ -168,11 +169,16 @@ def gpu_run(bk, ctx, ls, u_start, p_start, steps, warmup, torch, timing=True, u1
     return rows, ms[warmup:], delta, st
 
 
+def bordered_precond(P, N):
+    """P on the first N entries, identity on the border component (vectors of the MatrixFreeBLS system have N+1 entries)."""
+    return lambda r: P(r) if len(r) == N else np.concatenate([P(r[:N]), r[N:]])
+
+
 def cpu_steps(n, u_start, p_start, nsteps, workers):
     """CPU restatement (oracle/) of the same PALC steps; returns (rows, seconds)."""
     from oracle import problems, krylov, bls as obls, palc as opalc, precond as oprecond
     sh = problems.SwiftHohenberg((n, n), domain(n), l=PAR[0], nu=PAR[1])
-    Pinv = oprecond.dct_precond((n, n), domain(n), 1.0, workers=workers)
+    Pinv = bordered_precond(oprecond.dct_precond((n, n), domain(n), 1.0, workers=workers), n * n)
     ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
     prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=u_start, p0=p_start)
     cp = opalc.ContinuationPar(max_steps=nsteps, newton_options=opalc.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ols), **CONT)
@@ -183,8 +189,8 @@ def cpu_steps(n, u_start, p_start, nsteps, workers):
         return True
 
     t0 = time.perf_counter()
-    rows, st = opalc.continuation(prob, opalc.PALC(bls=obls.BorderingBLS(ols, check_precision=False)), cp, normC=opalc.norminf,
-                                  callback=cb)
+    obl = obls.MatrixFreeBLS(ols) if BLS["kind"] == "matrixfree" else obls.BorderingBLS(ols, check_precision=False)
+    rows, st = opalc.continuation(prob, opalc.PALC(bls=obl), cp, normC=opalc.norminf, callback=cb)
     t1 = time.perf_counter()
     # the first callback fires at step 0, i.e. after the two start-up Newton solves, which the metric excludes
     # (src/Continuation.jl:370-393): steps/sec is counted over the continuation! loop only
@@ -204,12 +210,14 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bls", default="matrixfree", choices=["matrixfree", "bordering"])
     args = ap.parse_args()
     n = args.grid
+    BLS["kind"] = args.bls
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"SH2d-fronts {n}x{n} fp64 on (lx, ly) = {n / 256:g} x (8 pi, 4 pi/sqrt 3), PALC (secant) + BorderingBLS + GMRES({GMRES['restart']}) reltol {GMRES['reltol']:g}, Pr = DCT (L1+I)^-1"
+    workload = f"SH2d-fronts {n}x{n} fp64 on (lx, ly) = {n / 256:g} x (8 pi, 4 pi/sqrt 3), PALC (secant) + {'MatrixFreeBLS' if args.bls == 'matrixfree' else 'BorderingBLS'} + GMRES({GMRES['restart']}) reltol {GMRES['reltol']:g}, Pr = DCT (L1+I)^-1"
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -221,7 +229,7 @@ def main():
         from oracle import problems, krylov, palc as opalc, precond as oprecond
         t_setup = time.perf_counter()
         sh = problems.SwiftHohenberg((n, n), domain(n), l=PAR[0], nu=PAR[1])
-        Pinv = oprecond.dct_precond((n, n), domain(n), 1.0, workers=cores)
+        Pinv = bordered_precond(oprecond.dct_precond((n, n), domain(n), 1.0, workers=cores), n * n)
         ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
         prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=sol0(n), p0=PAR[0])
         hexa = opalc.newton(prob, prob.u0, PAR[0], opalc.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ols), opalc.norminf)
@@ -266,7 +274,8 @@ def main():
             cp = P.ContinuationPar(max_steps=stride * rank + 1,
                                    newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls), **CONT)
             prob = P.BifurcationProblemB200(ctx, u_front, PAR, lens=0)
-            P.continuation(prob, P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False)), cp, normC=P.norminf, callback=grab)
+            sb = bk.MatrixFreeBLSB200(ls) if BLS["kind"] == "matrixfree" else bk.BorderingBLSB200(ls, check_precision=False)
+            P.continuation(prob, P.PALC(bls=sb), cp, normC=P.norminf, callback=grab)
             u_start, p_start, u1, p1 = grab.pair()
         ctx.sync()
         scout_ms = (time.perf_counter() - t0) * 1e3

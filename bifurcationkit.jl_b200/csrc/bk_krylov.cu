@@ -285,18 +285,27 @@ static inline void bk2_ensure_smem(K kern, size_t bytes, size_t* cur) {
   }
 }
 
-static bool fused2_available(const OpDesc& op) { return op.kind == BK_SH2D && !op.bordered && (op.nx % 2 == 0); }
+static bool fused2_available(const OpDesc& op) { return op.kind == BK_SH2D && (op.nx % 2 == 0); }
 
 static int launch_fused2(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* w, int j, double* hcol) {
   const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
   Plan2 p = plan2(c, (long long)tiles_x * op.ny, sh2_scratch_bytes);
   p.grid = tiles_x * ((op.ny + p.E - 1) / p.E);
   static size_t cur[BK2_EMAX + 1] = {0};
-  BK2_DISPATCH(p.E, {
-    bk2_ensure_smem(k2_fused<EE>, p.smem, &cur[EE]);
-    k2_fused<EE><<<p.grid, BK2_THREADS, p.smem, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
-                                                             c->counters + 0, hcol, c->gcoef, p.NS, p.sred_off);
-  });
+  static size_t curb[BK2_EMAX + 1] = {0};
+  if (op.bordered) {
+    BK2_DISPATCH(p.E, {
+      bk2_ensure_smem(k2_fused<EE, true>, p.smem, &curb[EE]);
+      k2_fused<EE, true><<<p.grid, BK2_THREADS, p.smem, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
+                                                                     c->counters + 0, hcol, c->gcoef, p.NS, p.sred_off);
+    });
+  } else {
+    BK2_DISPATCH(p.E, {
+      bk2_ensure_smem(k2_fused<EE, false>, p.smem, &cur[EE]);
+      k2_fused<EE, false><<<p.grid, BK2_THREADS, p.smem, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
+                                                                      c->counters + 0, hcol, c->gcoef, p.NS, p.sred_off);
+    });
+  }
   c->stats.kernel_launches++;
   BK_CUDA(c, cudaGetLastError());
   return BK_OK;
@@ -305,7 +314,9 @@ static int launch_fused2(bk_ctx* c, const OpDesc& op, const double* in, const do
 // ------------------------------------------------------------------------------------------------ host
 static inline int chunk_grid(long long n) { return (int)((n + BK_TILE - 1) / BK_TILE); }
 
-static bool fused_available(const OpDesc& op) { return (op.kind == BK_SH2D || op.kind == BK_SH3D) && !op.bordered; }
+static bool fused_available(const OpDesc& op) {
+  return ((op.kind == BK_SH2D || op.kind == BK_SH3D) && !op.bordered) || (op.kind == BK_SH2D && op.bordered && op.nx % 2 == 0);
+}
 
 static size_t dots_smem(int j) { return sizeof(double) * 8 * (size_t)(j > 0 ? j : 1); }
 

@@ -135,11 +135,21 @@ __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __re
 }
 
 // per-CTA partials of the j dot products + deterministic last-block reduction -> hcol[i] = s_i * sum, gcoef[i] = hcol[i] * s_i
+// With a border (bord != nullptr): row j of sred/partials carries <b, x_u>; the last CTA first forms
+// w_p = bscale * sum + bc * x_p, stores it as w[N], and adds V_i[N] * w_p to every dot product (vectors have N+1 entries).
+struct BorderFin {
+  double bscale, bc, xp;
+  double* w_tail;          // &w[N]
+  const double* V_tail;    // &V[0*ld + N]
+  long long ld;
+};
 __device__ __forceinline__ void dots_finish(int j, const double* sred, const double* __restrict__ scales,
                                             double* __restrict__ partials, unsigned int* counter, double* __restrict__ hcol,
-                                            double* __restrict__ gcoef, int* s_flag) {
+                                            double* __restrict__ gcoef, int* s_flag, const BorderFin* bord = nullptr,
+                                            double* s_wp = nullptr) {
   const int G = gridDim.x;
-  for (int i = threadIdx.x; i < j; i += blockDim.x) {
+  const int jj = bord ? j + 1 : j;
+  for (int i = threadIdx.x; i < jj; i += blockDim.x) {
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += sred[i * 8 + k];
@@ -147,11 +157,26 @@ __device__ __forceinline__ void dots_finish(int j, const double* sred, const dou
   }
   if (bk_last_block(counter, s_flag)) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double wp = 0.0;
+    if (bord) {
+      if (warp == 0) {
+        double t = 0.0;
+        for (int k = lane; k < G; k += 32) t += __ldcg(partials + (long long)j * G + k);
+        t = bk_warp_sum(t);
+        if (lane == 0) {
+          *s_wp = bord->bscale * t + bord->bc * bord->xp;
+          *bord->w_tail = *s_wp;
+        }
+      }
+      __syncthreads();
+      wp = *s_wp;
+    }
     for (int i = warp; i < j; i += nw) {
       double t = 0.0;
       for (int k = lane; k < G; k += 32) t += __ldcg(partials + (long long)i * G + k);
       t = bk_warp_sum(t);
       if (lane == 0) {
+        if (bord) t = fma(__ldg(bord->V_tail + (long long)i * bord->ld), wp, t);
         const double s = scales[i];
         const double h = s * t;
         hcol[i] = h;
@@ -170,9 +195,11 @@ struct Sh2Scratch {
   static constexpr size_t BYTES = sizeof(double) * (size_t)(V_ELEMS + Q_ELEMS);
 };
 
-template <int E>
+// BORDERED (MatrixFreeBLSmap, src/LinearBorderSolver.jl:312-325): val += x_p * a + shift * v, and *bsum accumulates this
+// thread's share of <b, x_u>.
+template <int E, bool BORDERED>
 __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __restrict__ in, double in_scale, int x0, int y0,
-                                              double* scratch, double (&val)[E]) {
+                                              double* scratch, double (&val)[E], double xp, double* bsum) {
   using S = Sh2Scratch<E>;
   double* vs = scratch;
   double* qs = scratch + S::V_ELEMS;
@@ -209,12 +236,17 @@ __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __
       const double uu = __ldg(op.u + gx + (long long)gy * nx);
       const double coef = l + uu * (2.0 * nu - 3.0 * uu);
       r = op.a0 * v + op.a1 * (coef * v - l1v);
+      if (BORDERED) {
+        const long long gi = gx + (long long)gy * nx;
+        r += xp * __ldg(op.ba + gi) + op.bshift * v;
+        *bsum = fma(__ldg(op.bb + gi), v, *bsum);
+      }
     }
     val[e] = r;
   }
 }
 
-template <int E>
+template <int E, bool BORDERED>
 static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, const double* __restrict__ in,
                                                                   const double* __restrict__ in_scale_ptr,
                                                                   double* __restrict__ w, const double* __restrict__ V,
@@ -245,7 +277,9 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
     for (int i = 0; i < npf; ++i)
       for (int r = 0; r < tl.rows; ++r) bulk_prefetch_l2(V + (long long)i * ld + tl.base + (long long)r * tl.rs, row_b);
   }
-  sh2_tile_eval<E>(op, in, s, x0, y0, smem2, val);
+  const double xp = BORDERED ? s * __ldg(in + op.N) : 0.0;
+  double bsum = 0.0;
+  sh2_tile_eval<E, BORDERED>(op, in, s, x0, y0, smem2, val, xp, &bsum);
   if (threadIdx.x < tl.len) {
 #pragma unroll
     for (int e = 0; e < E; ++e)
@@ -254,8 +288,23 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
   fence_proxy_async_smem();  // generic-proxy accesses to the scratch are ordered before the TMA writes that reuse it
   __syncthreads();           // scratch is dead, barriers are initialised: the ring takes over the shared memory
   stream_basis<E, 0>(tl, V, ld, j, ring, NS, &rg, val, sred, nullptr);
-  __syncthreads();
-  dots_finish(j, sred, scales, partials, counter, hcol, gcoef, &s_flag);
+  if (BORDERED) {
+    __shared__ double s_wp;
+    bsum = bk_warp_sum(bsum);  // bsum already carries the input scale (v = s * in)
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < BK2_CONS) sred[j * 8 + (threadIdx.x >> 5)] = bsum;
+    __syncthreads();
+    BorderFin bf;
+    bf.bscale = op.bscale;
+    bf.bc = op.bc;
+    bf.xp = xp;
+    bf.w_tail = w + op.N;
+    bf.V_tail = V + op.N;
+    bf.ld = ld;
+    dots_finish(j, sred, scales, partials, counter, hcol, gcoef, &s_flag, &bf, &s_wp);
+  } else {
+    __syncthreads();
+    dots_finish(j, sred, scales, partials, counter, hcol, gcoef, &s_flag);
+  }
 }
 
 __device__ __forceinline__ Tile2 linear_tile(long long n, int E) {

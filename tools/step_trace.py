@@ -15,4 +15,7 @@ def cb(st):
     print(f"step {st.step:3d} p={st.z_p:+.5f} ds={st.ds:+.2e} itn={st.itnewton} itl={st.itlinear:4d} work_lin={st.work_linear - last['wl']:4d} work_newton={st.work_newton - last['wn']:2d} fails={st.nfail - last['f']} ms={(now - t[0]) * 1e3:7.2f}", flush=True)
     last.update(f=st.nfail, wl=st.work_linear, wn=st.work_newton); t[0] = time.perf_counter()
     return True
-P.continuation(prob, P.PALC(bls=bk.BorderingBLSB200(ls, check_precision=False)), cp, normC=P.norminf, callback=cb)
+kind = sys.argv[3] if len(sys.argv) > 3 else "bordering"
+blsobj = bk.MatrixFreeBLSB200(ls) if kind == "matrixfree" else bk.BorderingBLSB200(ls, check_precision=False)
+print("bls:", kind)
+P.continuation(prob, P.PALC(bls=blsobj), cp, normC=P.norminf, callback=cb)
