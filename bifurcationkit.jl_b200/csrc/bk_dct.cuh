@@ -45,12 +45,13 @@ __device__ __forceinline__ int dct_pad(int i) { return i + (i >> 3); }
 
 // in-place DIT FFT of W lines of M complex points held bit-reversed in shared memory
 template <bool STRIDED>
-__device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, const double2* __restrict__ tw, bool inverse) {
+__device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, int logW, const double2* __restrict__ tw,
+                                        bool inverse) {
   int st = 0;
   if (logM & 1) {
     for (int b = threadIdx.x; b < (M >> 1) * W; b += blockDim.x) {
-      int line = STRIDED ? b % W : b / (M >> 1);
-      int bf = STRIDED ? b / W : b - line * (M >> 1);
+      int line = STRIDED ? (b & (W - 1)) : (b >> (logM - 1));
+      int bf = STRIDED ? (b >> logW) : (b & ((M >> 1) - 1));
       const int MP = DCT_PADDED(M);
       double2* p0 = STRIDED ? s + (long long)dct_pad(2 * bf) * W + line : s + (long long)line * MP + dct_pad(2 * bf);
       double2* p1 = STRIDED ? s + (long long)dct_pad(2 * bf + 1) * W + line : s + (long long)line * MP + dct_pad(2 * bf + 1);
@@ -65,8 +66,8 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, cons
     const int half = 1 << st;
     const int s1 = M >> (st + 1), s2 = M >> (st + 2);
     for (int g = threadIdx.x; g < (M >> 2) * W; g += blockDim.x) {
-      int line = STRIDED ? g % W : g / (M >> 2);
-      int gi = STRIDED ? g / W : g - line * (M >> 2);
+      int line = STRIDED ? (g & (W - 1)) : (g >> (logM - 2));
+      int gi = STRIDED ? (g >> logW) : (g & ((M >> 2) - 1));
       int grp = gi >> st, pos = gi & (half - 1);
       int i = (grp << (st + 2)) + pos;
       double2 w1 = __ldg(tw + pos * s1), w2 = __ldg(tw + pos * s2);
@@ -99,7 +100,7 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, cons
 // shared memory: s[M*W] complex, and for MODE 2 additionally cb[n*W] real
 template <bool STRIDED, int MODE>
 static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__ in, double* __restrict__ out, LineGeom g, int logM,
-                                                      int W, DctTables tb, SymbolArgs sy) {
+                                                      int W, int logW, DctTables tb, SymbolArgs sy) {
   extern __shared__ __align__(16) double2 sdct[];
   const int n = g.n, M = n >> 1;
   double2* s = sdct;
@@ -125,8 +126,8 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
   // ---------------- forward half (MODE 0, 2)
   if (MODE != 1) {
     for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
-      int line = STRIDED ? q % W : q / n;
-      int e = STRIDED ? q / W : q - line * n;
+      int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
+      int e = STRIDED ? (q >> logW) : (q & (n - 1));
       double xv = (line < nl) ? in[base + line * lstride + (long long)e * g.es] : 0.0;
       int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
       int p = dct_bitrev(m >> 1, logM);
@@ -134,10 +135,17 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
       sd[2 * ci + (m & 1)] = xv;
     }
     __syncthreads();
-    dct_fft<STRIDED>(s, M, logM, W, tb.tw, false);
+    dct_fft<STRIDED>(s, M, logM, W, logW, tb.tw, false);
     for (int q = threadIdx.x; q < (M + 1) * W; q += blockDim.x) {
-      int line = STRIDED ? q % W : q / (M + 1);
-      int k = STRIDED ? q / W : q - line * (M + 1);
+      // items 0 .. M*W-1 cover k < M (shift/mask indexing); the last W items are k = M of every line
+      int line, k;
+      if (q < M * W) {
+        line = STRIDED ? (q & (W - 1)) : (q >> logM);
+        k = STRIDED ? (q >> logW) : (q & (M - 1));
+      } else {
+        line = q - M * W;
+        k = M;
+      }
       if (line >= nl) continue;
       int k0 = k & (M - 1), k1 = (M - k) & (M - 1);
       double2 zk = STRIDED ? s[(long long)dct_pad(k0) * W + line] : s[(long long)line * MP + dct_pad(k0)];
@@ -169,8 +177,8 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
   // ---------------- inverse half (MODE 1, 2)
   if (MODE != 0) {
     for (int q = threadIdx.x; q < M * W; q += blockDim.x) {
-      int line = STRIDED ? q % W : q / M;
-      int k = STRIDED ? q / W : q - line * M;
+      int line = STRIDED ? (q & (W - 1)) : (q >> logM);
+      int k = STRIDED ? (q >> logW) : (q & (M - 1));
       double2 z = make_double2(0.0, 0.0);
       if (line < nl) {
         // V[j] = conj(dtw[j]) (C[j] - i C[n-j]),  C[n] = 0;  need j = k and j = M - k
@@ -202,10 +210,10 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
         s[(long long)line * MP + dct_pad(p)] = z;
     }
     __syncthreads();
-    dct_fft<STRIDED>(s, M, logM, W, tb.tw, true);
+    dct_fft<STRIDED>(s, M, logM, W, logW, tb.tw, true);
     for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
-      int line = STRIDED ? q % W : q / n;
-      int e = STRIDED ? q / W : q - line * n;
+      int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
+      int e = STRIDED ? (q >> logW) : (q & (n - 1));
       if (line >= nl) continue;
       int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
       long long ci = STRIDED ? (long long)dct_pad(m >> 1) * W + line : (long long)line * MP + dct_pad(m >> 1);

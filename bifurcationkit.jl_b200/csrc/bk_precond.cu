@@ -225,6 +225,7 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     if (W < 1) W = 1;
     if (W > 16) W = 16;
     if (env_w > 0) W = env_w;
+    while (W & (W - 1)) W &= W - 1;  // power of two (shift/mask indexing in the kernels)
     const int nthr = env_t > 0 ? env_t : 512;
     const int mode = fused_sym ? 2 : (dir > 0 ? 0 : 1);
     size_t sm = sizeof(double2) * (size_t)DCT_PADDED(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
@@ -245,17 +246,17 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     if (d == 0) {
       int grid = (g.nouter + W - 1) / W;
       if (mode == 0)
-        k_dct2<false, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<false, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
       else
-        k_dct2<false, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<false, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
     } else {
       dim3 grid((g.nx + W - 1) / W, g.nouter);
       if (mode == 0)
-        k_dct2<true, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<true, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
       else if (mode == 1)
-        k_dct2<true, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<true, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
       else
-        k_dct2<true, 2><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, tb, sy);
+        k_dct2<true, 2><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
     }
   } else {
     const double* M = pc.dense[d] + (dir > 0 ? 0 : (size_t)g.n * g.n);

@@ -14,6 +14,8 @@ import math
 
 import numpy as np
 
+from scipy.linalg import blas as _blas
+
 from .core import DeviceVec
 
 SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # src/Problems.jl:69
@@ -44,8 +46,9 @@ class V:
         """y <- a x + b y (VI.add!)"""
         if isinstance(y, DeviceVec):
             return y.axpby_(a, x, b)
-        y *= b
-        y += a * x
+        if b != 1.0:
+            _blas.dscal(b, y)
+        _blas.daxpy(x, y, a=a)  # in place (threaded BLAS-1, no temporaries)
         return y
 
     @staticmethod
@@ -53,7 +56,7 @@ class V:
         """x <- a x (VI.scale!)"""
         if isinstance(x, DeviceVec):
             return x.scale_(a)
-        x *= a
+        _blas.dscal(a, x)
         return x
 
     @staticmethod
