@@ -321,12 +321,13 @@ def main():
     clocks = sampler.stop()
     my_ms = float(np.sum(ms))
     nsteps = len(ms)
-    tt = torch.tensor([my_ms, float(nsteps)], dtype=torch.float64, device=f"cuda:{dev}")
+    tt = torch.tensor([my_ms, float(nsteps), scout_ms], dtype=torch.float64, device=f"cuda:{dev}")
     if dist:
         allt = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(allt, tt)
         tmax = max(float(t[0]) for t in allt)
         total_steps = int(sum(float(t[1]) for t in allt))
+        scout_ms = max(float(t[2]) for t in allt)
         # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear) per batch
         gathered = bk.segments.all_gather_rows(rows, args.steps + args.warmup + 1, dist, torch, f"cuda:{dev}")
         branch = bk.segments.merge_branch(gathered)
