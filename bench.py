@@ -97,6 +97,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of k2_fused from the committed `ncu --set full` capture
+    (profiles/r01c_ncu_k2_fused.csv; j ~ 16 at capture time: algorithmic 8N(j+2) + 16N border = 168 MB)."""
+    p = os.path.join(ROOT, "profiles", "r01c_ncu_k2_fused.csv")
+    try:
+        import csv
+        rows = list(csv.reader(open(p)))
+        h = rows[0]
+        vals = [float(r[h.index("dram__bytes_read.sum")]) + float(r[h.index("dram__bytes_write.sum")]) for r in rows[2:]]
+        return {"bytes_per_launch": 1e6 * sum(vals) / len(vals), "source": "profiles/r01c_ncu_k2_fused.csv (k2_fused, one ncu --set full capture)"}
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -347,9 +361,9 @@ def main():
     peak, peak_src = measured_peak()
     fused_ms, fused_b, fused_l = delta.get("total_fused_ms", 0.0), delta.get("total_fused_bytes", 0), delta.get("total_fused_launches", 0)
     ach = (fused_b / 1e9) / (fused_ms * 1e-3) if fused_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_fused_jvp_dots<2> + k_update_norm (fused JVP+Arnoldi step, 2 launches/step)",
+    roofline = {"bound": "hbm", "kernel": "k2_fused<E,bordered> + k2_update<E> (fused JVP+Arnoldi step = 2 launches per Krylov iteration; TMA ring)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src,
-                "traffic": None, "launches": int(fused_l), "avg_launch_us": (fused_ms * 1e3 / fused_l) if fused_l else None,
+                "traffic": ncu_traffic(), "launches": int(fused_l), "avg_launch_us": (fused_ms * 1e3 / fused_l) if fused_l else None,
                 "algorithmic_bytes_per_launch": (fused_b / fused_l) if fused_l else None,
                 "share_of_step": (fused_ms / my_ms) if my_ms else None}
 

@@ -17,6 +17,7 @@
 // normalisation costs no memory pass ("deferred as a scalar") and the host never has to be in the
 // loop to launch the next step: Givens rotations run on the host one iteration behind the GPU.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "bk_common.cuh"
@@ -245,6 +246,14 @@ static Plan2 plan2(bk_ctx* c, long long units_of_256, size_t scratch_bytes_per_E
   if (E < 1) E = 1;
   if (E > BK2_EMAX) E = BK2_EMAX;
   if (force_E) E = force_E;
+  {
+    static int env_e = -1;
+    if (env_e < 0) {
+      const char* a = getenv("BK2_E");
+      env_e = a ? atoi(a) : 0;
+    }
+    if (env_e >= 1 && env_e <= BK2_EMAX) E = env_e;  // tuning override
+  }
   p.E = (int)E;
   p.grid = (int)((units_of_256 + E - 1) / E);
   const size_t sred = sizeof(double) * 8 * (size_t)(c->m + 2);

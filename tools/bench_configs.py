@@ -81,9 +81,10 @@ if "5" in which:
     s0 = s0 - s0.min(); s0 = s0 / s0.max() * 1.2
     ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
     ls = bk.GMRESB200(reltol=1e-9, restart=150, maxiter=150, Pr=True, orth="cgs2")  # rtol of examples/SH3d.jl:93
+    ls_newton = bk.GMRESB200(reltol=1e-4, restart=150, maxiter=150, Pr=True)
     prob = P.BifurcationProblemB200(ctx, ctx.to_device(s0.reshape(-1)), (0.1, 1.2), lens=0)
     ctx.sync(); t0 = time.perf_counter()
-    sol = P.newton(prob, prob.u0, 0.1, P.NewtonPar(tol=1e-8, max_iterations=25, linsolver=ls), P.norminf)
+    sol = P.newton(prob, prob.u0, 0.1, P.NewtonPar(tol=1e-8, max_iterations=80, linsolver=ls_newton), P.norminf)
     ctx.sync(); t_newton = time.perf_counter() - t0
     eig = bk.ShiftInvertB200(0.1, ls, krylovdim=40, tol=1e-8, maxrestart=5)
     J = ctx.jacobian(sol.u)
