@@ -94,6 +94,8 @@ struct bk_ctx {
   std::vector<std::pair<size_t, double*>> vec_pool;
   // eigensolver workspace (lazily allocated)
   double* Q = nullptr;       // (qcap+1) x ld Arnoldi basis of the shift-invert operator
+  double* Q2 = nullptr;      // second basis buffer for thick restarts
+  int q2cap = 0;
   int qcap = 0;
   double* eig_dev = nullptr; // ones (qcap+2) | hcolA (qcap+2) | hcolB (qcap+2) | g (qcap+2) | coef (2*(qcap+2))
   double* eig_pinned = nullptr;

@@ -138,7 +138,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   double* bufs[] = {c->u_state, c->V, c->w, c->z, c->r, c->scales, c->gcoef, c->hcols, c->hcols2, c->partials,
-                    c->red_out, c->phi, c->xpi, c->fcache, c->pc.work, c->pc.work2, c->pc.tri, c->Q, c->eig_dev};
+                    c->red_out, c->phi, c->xpi, c->fcache, c->pc.work, c->pc.work2, c->pc.tri, c->Q, c->Q2, c->eig_dev};
   for (double* b : bufs)
     if (b) cudaFree(b);
   for (int d = 0; d < 3; ++d) {

@@ -31,6 +31,11 @@ struct SymbolArgs {
   const double* lam_x;  // eigenvalues along x (index = global x of the line), may be NULL
   const double* lam_o;  // eigenvalues along the outer index, may be NULL
   double shift;         // symbol = (1 + lam_e + lam_x + lam_o)^2 + shift
+  // optional pass-through of trailing entries (bordered vectors: the preconditioner is the identity on the border);
+  // done by one thread of the kernel instead of a separate 8-byte memcpy on the copy engine
+  const double* tail_src;
+  double* tail_dst;
+  int tail_n;
 };
 
 __device__ __forceinline__ double2 dct_cmul(double2 a, double2 b) {
@@ -122,6 +127,7 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
     lstride = g.os;
   }
   const double inv_m = 1.0 / M;
+  if (sy.tail_n > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < sy.tail_n) sy.tail_dst[threadIdx.x] = sy.tail_src[threadIdx.x];
 
   // ---------------- forward half (MODE 0, 2)
   if (MODE != 1) {

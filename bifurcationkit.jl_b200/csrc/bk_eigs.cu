@@ -178,6 +178,44 @@ extern "C" int32_t bk_hessenberg_eig(const double* H, int32_t n, int32_t ldh, do
   return BK_OK;
 }
 
+// Symmetric eigen-decomposition by cyclic Jacobi rotations: A (n x n, column-major, overwritten) = S diag(w) S^T.
+static void jacobi_eig(std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& S) {
+  S.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) S[i + (size_t)i * n] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, dg = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) (i == j ? dg : off) += A[i + (size_t)j * n] * A[i + (size_t)j * n];
+    if (off <= 1e-32 * (dg + 1e-300)) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        double apq = A[p + (size_t)q * n];
+        if (apq == 0.0) continue;
+        double app = A[p + (size_t)p * n], aqq = A[q + (size_t)q * n];
+        double th = (aqq - app) / (2.0 * apq);
+        double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+        double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < n; ++k) {  // columns p, q
+          double akp = A[k + (size_t)p * n], akq = A[k + (size_t)q * n];
+          A[k + (size_t)p * n] = cs * akp - sn * akq;
+          A[k + (size_t)q * n] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // rows p, q
+          double apk = A[p + (size_t)k * n], aqk = A[q + (size_t)k * n];
+          A[p + (size_t)k * n] = cs * apk - sn * aqk;
+          A[q + (size_t)k * n] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          double skp = S[k + (size_t)p * n], skq = S[k + (size_t)q * n];
+          S[k + (size_t)p * n] = cs * skp - sn * skq;
+          S[k + (size_t)q * n] = sn * skp + cs * skq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; ++i) w[i] = A[i + (size_t)i * n];
+}
+
 static __global__ void k_fill_ones(double* p, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 1.0;
@@ -243,7 +281,107 @@ extern "C" int32_t bk_eigs_shift_invert(bk_ctx* c, double sigma, int32_t nev, in
   std::vector<std::vector<cplx>> Y(nev);
   bool converged = false;
   int keff = m;
-  for (int rs = 0; rs < maxrestart && !converged; ++rs) {
+  // ---------------- symmetric operators (Swift-Hohenberg): thick-restart (Krylov-Schur with Ritz vectors) ----------------
+  const bool sym = (c->kind == BK_SH2D || c->kind == BK_SH3D);
+  std::vector<double> Ssym, wsym;
+  std::vector<int> order;
+  if (sym) {
+    if (!c->Q2 || c->q2cap < m) {
+      BK_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (c->Q2) cudaFree(c->Q2);
+      BK_CUDA(c, cudaMalloc(&c->Q2, 8 * (size_t)c->ld * (m + 1)));
+      c->q2cap = m;
+    }
+    std::fill(H.begin(), H.end(), 0.0);
+    BK_TRY(bk_launch_update(c, c->Q, gco, x, n, 0, c->Q, hA, hB));
+    BK_CUDA(c, cudaMemcpyAsync(hp, hA, 8, cudaMemcpyDeviceToHost, c->stream));
+    BK_CUDA(c, cudaStreamSynchronize(c->stream));
+    BK_CHECK(c, hp[0] > 0, "zero start vector");
+    BK_TRY(bk_dev_scale(c, c->Q, 1.0 / hp[0], n));
+    int kstart = 0;
+    for (int rs = 0; rs < maxrestart && !converged; ++rs) {
+      keff = m;
+      for (int k = kstart; k < m; ++k) {
+        const int j = k + 1;
+        int cv = 0, it = 0;
+        int st = bk_gmres_dev(c, op, c->Q + (size_t)k * c->ld, x, inner, &cv, &it, nullptr);
+        if (st < 0) return st;
+        ++total_ops;
+        double* qn = c->Q + (size_t)(k + 1) * c->ld;
+        BK_TRY(bk_launch_dots(c, c->Q, ones, x, n, j, hA, gco));
+        BK_TRY(bk_launch_update(c, c->Q, gco, x, n, j, qn, hA + j, hB + S - 1));
+        BK_TRY(bk_launch_dots(c, c->Q, ones, qn, n, j, hB, gco));
+        BK_TRY(bk_launch_update(c, c->Q, gco, qn, n, j, qn, hA + j, hB + S - 1));
+        BK_CUDA(c, cudaMemcpyAsync(hp, hA, 8 * (size_t)(2 * S), cudaMemcpyDeviceToHost, c->stream));
+        BK_CUDA(c, cudaStreamSynchronize(c->stream));
+        double cn = 0;
+        for (int i = 0; i < j; ++i) {
+          H[i + (size_t)k * (m + 1)] = hp[i] + hp[S + i];
+          cn = fmax(cn, fabs(H[i + (size_t)k * (m + 1)]));
+        }
+        double hk1 = hp[j];
+        H[j + (size_t)k * (m + 1)] = hk1;
+        if (!(hk1 > 1e-14 * fmax(cn, 1e-300))) {
+          keff = k + 1;
+          break;
+        }
+        BK_TRY(bk_dev_scale(c, qn, 1.0 / hk1, n));
+      }
+      // symmetrised projected matrix (exactly symmetric in exact arithmetic)
+      std::vector<double> A((size_t)keff * keff);
+      for (int jj = 0; jj < keff; ++jj)
+        for (int i = 0; i < keff; ++i) {
+          double hij = (i <= jj + 1 || jj < kstart) ? H[i + (size_t)jj * (m + 1)] : 0.0;
+          double hji = (jj <= i + 1 || i < kstart) ? H[jj + (size_t)i * (m + 1)] : 0.0;
+          // below-diagonal entries of Arnoldi columns other than the sub-diagonal are zero; the arrow row of a
+          // restarted factorisation is stored in row kstart of the retained columns
+          A[i + (size_t)jj * keff] = (i == jj) ? hij : ((i < jj) ? hij : hji);
+        }
+      for (int jj = 0; jj < keff; ++jj)
+        for (int i = jj + 1; i < keff; ++i) A[i + (size_t)jj * keff] = A[jj + (size_t)i * keff];
+      jacobi_eig(A, keff, wsym, Ssym);
+      order.resize(keff);
+      for (int i = 0; i < keff; ++i) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return fabs(wsym[a]) > fabs(wsym[b]); });
+      const double hlast = (keff == m) ? H[m + (size_t)(m - 1) * (m + 1)] : 0.0;
+      int nv = std::min<int>(nev, keff);
+      bool all = true;
+      for (int q = 0; q < nv; ++q) {
+        const int iq = order[q];
+        ritz[q] = cplx(wsym[iq], 0.0);
+        Y[q].assign(keff, cplx(0, 0));
+        for (int i = 0; i < keff; ++i) Y[q][i] = cplx(Ssym[i + (size_t)iq * keff], 0.0);
+        double resid = fabs(hlast) * fabs(Ssym[(keff - 1) + (size_t)iq * keff]);
+        if (resid > tol * fmax(fabs(wsym[iq]), 1e-300)) all = false;
+      }
+      for (int q = nv; q < nev; ++q) ritz[q] = cplx(0, 0);
+      converged = all || keff < m;
+      if (!converged && rs + 1 < maxrestart) {
+        int pkeep = std::min(keff - 2, nev + std::max(8, (m - nev) / 3));
+        if (pkeep < 1) pkeep = 1;
+        for (int q = 0; q < pkeep; ++q) {  // Q2_q = Q S[:, order[q]]
+          for (int i = 0; i < keff; ++i) hp[i] = Ssym[i + (size_t)order[q] * keff];
+          BK_CUDA(c, cudaMemcpyAsync(coef, hp, 8 * (size_t)keff, cudaMemcpyHostToDevice, c->stream));
+          BK_TRY(bk_launch_lincomb(c, c->Q, nullptr, c->Q2 + (size_t)q * c->ld, 0.0, n, keff, coef));
+          BK_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        BK_TRY(bk_dev_copy(c, c->Q2 + (size_t)pkeep * c->ld, c->Q + (size_t)keff * c->ld, n));  // residual direction q_{m+1}
+        BK_CUDA(c, cudaMemcpyAsync(c->Q, c->Q2, 8 * (size_t)c->ld * (pkeep + 1), cudaMemcpyDeviceToDevice, c->stream));
+        std::vector<double> bnew(pkeep), thnew(pkeep);
+        for (int q = 0; q < pkeep; ++q) {
+          thnew[q] = wsym[order[q]];
+          bnew[q] = hlast * Ssym[(keff - 1) + (size_t)order[q] * keff];
+        }
+        std::fill(H.begin(), H.end(), 0.0);
+        for (int q = 0; q < pkeep; ++q) {
+          H[q + (size_t)q * (m + 1)] = thnew[q];
+          H[pkeep + (size_t)q * (m + 1)] = bnew[q];
+        }
+        kstart = pkeep;
+      }
+    }
+  }
+  for (int rs = 0; !sym && rs < maxrestart && !converged; ++rs) {
     std::fill(H.begin(), H.end(), 0.0);
     // Q_0 = x / ||x||
     BK_TRY(bk_launch_update(c, c->Q, gco, x, n, 0, c->Q, hA, hB));

@@ -231,7 +231,7 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     size_t sm = sizeof(double2) * (size_t)DCT_PADDED(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
     int logM = ilog2(g.n / 2);
     DctTables tb{pc.tw[d], pc.wn[d], pc.dtw[d]};
-    SymbolArgs sy{nullptr, nullptr, nullptr, 0.0};
+    SymbolArgs sy{nullptr, nullptr, nullptr, 0.0, nullptr, nullptr, 0};
     if (fused_sym) sy = *fused_sym;
     static bool attr = false;
     if (!attr) {
@@ -279,6 +279,7 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
   BK_CHECK(c, pc.kind != BK_PC_NONE, "no preconditioner set up (bk_precond_setup)");
   BK_CHECK(c, in != out, "preconditioner: in-place application is not supported");
   const long long N = c->N;
+  bool tail_done = false;
   if (pc.kind == BK_PC_SH_DCT) {
     const int nx = (int)c->dims[0], ny = (int)c->dims[1], nz = c->kind == BK_SH3D ? (int)c->dims[2] : 1;
     const int nd = c->kind == BK_SH3D ? 3 : 2;
@@ -287,7 +288,13 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
     const int last = nd - 1;
     if (pc.pow2[last]) {
       // x fwd, [y fwd,] (last dim: fwd + symbol + inverse in one kernel), [y inv,] x inv
-      SymbolArgs sy{pc.lam[last], pc.lam[0], nd == 3 ? pc.lam[1] : nullptr, pc.a0};
+      SymbolArgs sy{pc.lam[last], pc.lam[0], nd == 3 ? pc.lam[1] : nullptr, pc.a0, nullptr, nullptr, 0};
+      if (n > N && n - N <= 32) {  // border entries ride along with the fused kernel
+        sy.tail_src = in + N;
+        sy.tail_dst = out + N;
+        sy.tail_n = (int)(n - N);
+        tail_done = true;
+      }
       BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
       if (nd == 3) {
         BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
@@ -338,7 +345,8 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
     c->stats.kernel_launches++;
     BK_CUDA(c, cudaGetLastError());
   }
-  if (n > N) BK_CUDA(c, cudaMemcpyAsync(out + N, in + N, 8 * (size_t)(n - N), cudaMemcpyDeviceToDevice, c->stream));
+  if (n > N && !tail_done)
+    BK_CUDA(c, cudaMemcpyAsync(out + N, in + N, 8 * (size_t)(n - N), cudaMemcpyDeviceToDevice, c->stream));
   return BK_OK;
 }
 
