@@ -429,8 +429,10 @@ struct TimerScope {
 static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, long long n, int k, size_t* timer_slot) {
   const int j = k + 1;
   const int mh = c->m + 4;
-  double* hcol = c->hcols + (size_t)k * mh;
-  double* hcol2 = c->hcols2 + (size_t)k * mh;
+  // The H column is written by the kernels' last CTA straight into pinned, device-mapped host memory (UVA): no
+  // D2H memcpy on the copy engine sits between two Arnoldi steps of the same stream any more.
+  double* hcol = c->h_pinned + (size_t)k * mh;
+  double* hcol2 = c->h_pinned + (size_t)(c->m + 1) * mh + (size_t)k * mh;
   const double* in = c->V + (size_t)k * c->ld;
   const double* sp = c->scales + k;
   const bool left = o->pc_side == BK_SIDE_LEFT && c->pc.kind != BK_PC_NONE;
@@ -467,11 +469,6 @@ static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lon
     BK_TRY(launch_dots(c, vnext, n, j, hcol2));
     BK_TRY(launch_update(c, vnext, n, j, vnext, hcol + j, c->scales + k + 1));
   }
-  size_t bytes = sizeof(double) * (size_t)(j + 1);
-  BK_CUDA(c, cudaMemcpyAsync(c->h_pinned + (size_t)k * mh, hcol, bytes, cudaMemcpyDeviceToHost, c->stream));
-  if (o->orth == BK_ORTH_CGS2)
-    BK_CUDA(c, cudaMemcpyAsync(c->h_pinned + (size_t)(c->m + 1) * mh + (size_t)k * mh, hcol2, sizeof(double) * j,
-                               cudaMemcpyDeviceToHost, c->stream));
   BK_CUDA(c, cudaEventRecord(c->events[k], c->stream));
   c->stats.last_fused_bytes += 8LL * n * (2LL * j + 4);
   c->stats.last_fused_launches += 2;
