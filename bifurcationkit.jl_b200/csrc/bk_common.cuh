@@ -160,6 +160,31 @@ int bk_launch_lincomb(bk_ctx* c, const double* basis, const double* scales, doub
                       const double* coef_dev);
 int bk_tmp(bk_ctx* c, int slot, double** out);  // lazily allocated ld-sized temporaries
 
+// ---- programmatic dependent launch (PDL): the next kernel of the stream is launched while this one drains ---------
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t bk_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+// first statement of every kernel launched through bk_launch_pdl: wait for the previous grid's memory, then let the next
+// grid start launching (its CTAs block at their own wait)
+__device__ __forceinline__ void bk_pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ double bk_warp_sum(double v) {

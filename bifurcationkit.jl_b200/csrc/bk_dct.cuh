@@ -106,6 +106,7 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, int 
 template <bool STRIDED, int MODE>
 static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__ in, double* __restrict__ out, LineGeom g, int logM,
                                                       int W, int logW, DctTables tb, SymbolArgs sy) {
+  bk_pdl_sync();
   extern __shared__ __align__(16) double2 sdct[];
   const int n = g.n, M = n >> 1;
   double2* s = sdct;

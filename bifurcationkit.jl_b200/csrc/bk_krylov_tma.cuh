@@ -254,6 +254,7 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
                                                                   double* __restrict__ partials, unsigned int* counter,
                                                                   double* __restrict__ hcol, double* __restrict__ gcoef,
                                                                   int NS, int sred_off) {
+  bk_pdl_sync();
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
   __shared__ int s_flag;
@@ -328,6 +329,7 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_dots(const double* _
                                                                  double* __restrict__ partials, unsigned int* counter,
                                                                  double* __restrict__ hcol, double* __restrict__ gcoef, int NS,
                                                                  int sred_off) {
+  bk_pdl_sync();
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
   __shared__ int s_flag;
@@ -354,6 +356,7 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_update(const double*
                                                                    double* __restrict__ partials, unsigned int* counter,
                                                                    double* __restrict__ h_out, double* __restrict__ scale_out,
                                                                    int NS) {
+  bk_pdl_sync();
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
   __shared__ double s_w[9];

@@ -246,17 +246,17 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     if (d == 0) {
       int grid = (g.nouter + W - 1) / W;
       if (mode == 0)
-        k_dct2<false, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
+        bk_launch_pdl(k_dct2<false, 0>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
       else
-        k_dct2<false, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
+        bk_launch_pdl(k_dct2<false, 1>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
     } else {
       dim3 grid((g.nx + W - 1) / W, g.nouter);
       if (mode == 0)
-        k_dct2<true, 0><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
+        bk_launch_pdl(k_dct2<true, 0>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
       else if (mode == 1)
-        k_dct2<true, 1><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
+        bk_launch_pdl(k_dct2<true, 1>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
       else
-        k_dct2<true, 2><<<grid, nthr, sm, c->stream>>>(in, out, g, logM, W, ilog2(W), tb, sy);
+        bk_launch_pdl(k_dct2<true, 2>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
     }
   } else {
     const double* M = pc.dense[d] + (dir > 0 ? 0 : (size_t)g.n * g.n);

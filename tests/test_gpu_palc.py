@@ -186,3 +186,33 @@ def test_shift_invert_eigs_cgl_complex(bk):
     key = lambda z: (-round(z.real, 7), -z.imag)
     assert cv
     assert np.allclose(sorted(vals, key=key), sorted(ref, key=key), atol=1e-6)
+
+
+def test_potrap_bordered_matrixfree_solve_vs_dense(bk):
+    """Config 4 (cGL2d Trapeze, bordered matrix-free solve) at a size where the dense Jacobian of the PO functional can be
+    assembled column by column with the oracle: MatrixFreeBLS(GMRES) on po_jvp == dense bordered solve."""
+    from oracle import potrap as opotrap
+    Nx, Ny, M = 8, 6, 5
+    gl = problems.GinzburgLandau2D(Nx, Ny, np.pi, np.pi / 2, r=1.4)
+    rng = np.random.default_rng(21)
+    NM = gl.N * M
+    N = NM + 1
+    x = np.concatenate([0.4 * rng.standard_normal(NM), [5.9]])
+    phi, xpi = rng.standard_normal(NM), rng.standard_normal(NM)
+    tr = opotrap.Trapeze(gl.F, gl.dF, phi, xpi, M, gl.N)
+    Jd = np.column_stack([tr.jvp(x, e) for e in np.eye(N)])
+    dR, dzu, R = rng.standard_normal(N), rng.standard_normal(N), rng.standard_normal(N)
+    dzp, nn, xiu, xip = 0.8, -0.3, 0.5, 0.5
+    A = np.zeros((N + 1, N + 1))
+    A[:N, :N] = Jd
+    A[:N, N] = dR
+    A[N, :N] = xiu * dzu / N
+    A[N, N] = xip * dzp
+    ref = np.linalg.solve(A, np.concatenate([R, [nn]]))
+    ctx = bk.Context(bk.BK_POTRAP_CGL2D, (Nx, Ny, M), (np.pi, np.pi / 2), krylov_m=N + 1, params=(1.4, 0.1, 1.0, -1.0, 1.0))
+    ctx.potrap_set_section(phi, xpi)
+    J = ctx.jacobian(x)
+    ls = bk.GMRESB200(reltol=1e-11, restart=N + 1, maxiter=N + 1, orth="cgs2")
+    dX, dl, ok, it = bk.MatrixFreeBLSB200(ls)(J, dR, dzu, dzp, R, nn, xiu, xip, dotscale=1.0 / N)
+    assert ok
+    assert _rel(dX, ref[:N]) < 1e-7 and abs(dl - ref[N]) < 1e-7 * max(1.0, abs(ref[N]))
