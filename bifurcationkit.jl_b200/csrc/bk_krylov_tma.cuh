@@ -107,29 +107,57 @@ __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __re
     }
   } else {
     const int t = threadIdx.x;
-    for (int i = 0; i < j; ++i) {
-      const int s = i % NS;
-      mbar_wait(&rg->full[s], (unsigned)((i / NS) & 1));
-      const double* st = ring + (size_t)s * (E * BK2_ROW) + t;
-      if (MODE == 0) {
-        double a = 0.0;
+    if (MODE == 0) {
+      // two basis vectors per trip: their warp reductions are independent shuffle chains that overlap
+      for (int i = 0; i < j; i += 2) {
+        const int s0 = i % NS, s1 = (i + 1) % NS;
+        const bool two = (i + 1 < j);
+        mbar_wait(&rg->full[s0], (unsigned)((i / NS) & 1));
+        const double* st0 = ring + (size_t)s0 * (E * BK2_ROW) + t;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
-          if (e < tl.rows && t < lim) a = fma(st[e * BK2_ROW], val[e], a);
+          if (e < tl.rows && t < lim) a0 = fma(st0[e * BK2_ROW], val[e], a0);
         }
-        a = bk_warp_sum(a);
-        if (lane == 0) sred[i * 8 + warp] = a;
-      } else {
+        if (two) {
+          mbar_wait(&rg->full[s1], (unsigned)(((i + 1) / NS) & 1));
+          const double* st1 = ring + (size_t)s1 * (E * BK2_ROW) + t;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
+            if (e < tl.rows && t < lim) a1 = fma(st1[e * BK2_ROW], val[e], a1);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&rg->empty[s0]);
+          if (two) mbar_arrive(&rg->empty[s1]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        if (lane == 0) {
+          sred[i * 8 + warp] = a0;
+          if (two) sred[(i + 1) * 8 + warp] = a1;
+        }
+      }
+    } else {
+      for (int i = 0; i < j; ++i) {
+        const int s = i % NS;
+        mbar_wait(&rg->full[s], (unsigned)((i / NS) & 1));
+        const double* st = ring + (size_t)s * (E * BK2_ROW) + t;
         const double g = __ldg(gcoef + i);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
           if (e < tl.rows && t < lim) val[e] = fma(-g, st[e * BK2_ROW], val[e]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg->empty[s]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg->empty[s]);
     }
   }
 }
