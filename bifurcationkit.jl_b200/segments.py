@@ -22,14 +22,20 @@ class SeedGrabber:
     def __init__(self, rank, stride, copy):
         self.a, self.b = seed_steps(rank, stride)
         self.copy, self.seeds = copy, {}
+        self.last = []  # the two most recent scout points: fallback seeds if the branch ends before step b
 
     def __call__(self, st):
         if st.step in (self.a, self.b):
             self.seeds[st.step] = (self.copy(st.z_u), st.z_p)
+        self.last = (self.last + [(st.step, self.copy(st.z_u), st.z_p)])[-2:]  # a device copy per scout step: negligible
         return st.step < self.b
 
     def pair(self):
-        (u0, p0), (u1, p1) = self.seeds[self.a], self.seeds[self.b]
+        if self.a in self.seeds and self.b in self.seeds:
+            (u0, p0), (u1, p1) = self.seeds[self.a], self.seeds[self.b]
+            return u0, p0, u1, p1
+        # the scout stopped early (parameter bound reached / ds < dsmin): seed from its last two points
+        (_, u0, p0), (_, u1, p1) = self.last
         return u0, p0, u1, p1
 
 
