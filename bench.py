@@ -270,6 +270,12 @@ def main():
         # size take minutes on CPU, so the sample starts from the front guess relaxed on the CPU with the same solver.
         from oracle import problems, krylov, palc as opalc, precond as oprecond
         t_setup = time.perf_counter()
+        nthr, limiter = best_blas_threads(n * n, cores)
+        if limiter is not None:
+            limiter(limits=nthr, user_api="blas")
+
+        # (the BLAS thread count is calibrated BEFORE the start-up solves: with one BLAS thread per core of a 128-core host
+        # the two Newton solves below took 10 minutes, with the calibrated count about half a minute)
         sh = problems.SwiftHohenberg((n, n), domain(n), l=PAR[0], nu=PAR[1])
         Pinv = bordered_precond(oprecond.dct_precond((n, n), domain(n), 1.0, workers=cores), n * n)
         ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
@@ -277,6 +283,7 @@ def main():
         hexa = opalc.newton(prob, prob.u0, PAR[0], opalc.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ols), opalc.norminf)
         fr = opalc.newton(prob, front_guess(hexa.u, n), PAR[0], opalc.NewtonPar(tol=1e-9, max_iterations=30, linsolver=ols),
                           opalc.norminf)
+        assert fr.converged, fr.residuals
         t_setup = time.perf_counter() - t_setup
         k = max(1, min(args.steps, args.cpu_steps))
         rows, secs, nst = cpu_steps(n, fr.u, PAR[0], k, cores)
