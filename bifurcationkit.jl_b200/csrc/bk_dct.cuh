@@ -241,14 +241,28 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
 
   // ---------------- forward half (MODE 0, 2)
   if (MODE != 1) {
-    for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
-      int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
-      int e = STRIDED ? (q >> logW) : (q & (n - 1));
-      double xv = (line < nl) ? in[base + line * lstride + (long long)e * g.es] : 0.0;
-      int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
-      int p = m >> 1;  // natural order (Stockham FFT)
-      long long ci = STRIDED ? (long long)dct_pad(p) * W + line : (long long)line * MP + dct_pad(p);
-      sd[2 * ci + (m & 1)] = xv;
+    // batches of 8 independent global loads per thread (one load latency per batch instead of per element)
+    for (int q0 = threadIdx.x; q0 < n * W; q0 += 8 * blockDim.x) {
+      double xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + u * blockDim.x;
+        const int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
+        const int e = STRIDED ? (q >> logW) : (q & (n - 1));
+        xv[u] = (q < n * W && line < nl) ? __ldg(in + base + line * lstride + (long long)e * g.es) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + u * blockDim.x;
+        if (q < n * W) {
+          const int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
+          const int e = STRIDED ? (q >> logW) : (q & (n - 1));
+          const int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
+          const int p = m >> 1;  // natural order (Stockham FFT)
+          const long long ci = STRIDED ? (long long)dct_pad(p) * W + line : (long long)line * MP + dct_pad(p);
+          sd[2 * ci + (m & 1)] = xv[u];
+        }
+      }
     }
     __syncthreads();
     dct_fft_sk<STRIDED>(s, M, logM, W, logW, tb.tw, false);
@@ -292,6 +306,7 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
   }
   // ---------------- inverse half (MODE 1, 2)
   if (MODE != 0) {
+#pragma unroll 4
     for (int q = threadIdx.x; q < M * W; q += blockDim.x) {
       int line = STRIDED ? (q & (W - 1)) : (q >> logM);
       int k = STRIDED ? (q >> logW) : (q & (M - 1));
@@ -302,10 +317,10 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
         double ck, cnk, cj, cnj;
         if (MODE == 1) {
           long long gb = base + line * lstride;
-          ck = in[gb + (long long)k * g.es];
-          cnk = k > 0 ? in[gb + (long long)(n - k) * g.es] : 0.0;
-          cj = in[gb + (long long)j2 * g.es];
-          cnj = in[gb + (long long)(n - j2) * g.es];  // j2 >= 1 always (k < M)
+          ck = __ldg(in + gb + (long long)k * g.es);
+          cnk = k > 0 ? __ldg(in + gb + (long long)(n - k) * g.es) : 0.0;
+          cj = __ldg(in + gb + (long long)j2 * g.es);
+          cnj = __ldg(in + gb + (long long)(n - j2) * g.es);  // j2 >= 1 always (k < M)
         } else {
           ck = cb[(long long)k * W + line];
           cnk = k > 0 ? cb[(long long)(n - k) * W + line] : 0.0;
