@@ -102,115 +102,6 @@ __device__ __forceinline__ void dct_fft(double2* s, int M, int logM, int W, int 
   }
 }
 
-// ---- Stockham autosort FFT (natural order in and out), radix 8/4/2 passes held in registers ------------------------------
-// One thread owns 8 complex values per pass (one radix-8, two radix-4 or four radix-2 butterflies); blockDim.x == M*W/8.
-// tw8[k] = exp(-2 pi i k / M), k < M (full circle).  Two block barriers per pass; log8(M) passes (3 for a 1024-point DCT).
-__device__ __forceinline__ void sk_fft2(double2& a, double2& b) {
-  double2 t = a;
-  a = make_double2(t.x + b.x, t.y + b.y);
-  b = make_double2(t.x - b.x, t.y - b.y);
-}
-// multiply by s*i (s = -1 forward, +1 inverse)
-__device__ __forceinline__ double2 sk_muli(double2 a, bool inverse) { return inverse ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }
-__device__ __forceinline__ void sk_fft4(double2& v0, double2& v1, double2& v2, double2& v3, bool inverse) {
-  sk_fft2(v0, v2);
-  sk_fft2(v1, v3);
-  v3 = sk_muli(v3, inverse);
-  sk_fft2(v0, v1);
-  sk_fft2(v2, v3);
-  double2 t = v1;  // natural order: X0=v0, X1=v2, X2=v1, X3=v3
-  v1 = v2;
-  v2 = t;
-}
-__device__ __forceinline__ void sk_fft8(double2 (&v)[8], bool inverse) {
-  const double r = 0.70710678118654752440;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) sk_fft2(v[k], v[k + 4]);
-  // differences times W8^n, W8 = exp(s i pi/4)
-  double2 t5 = v[5], t7 = v[7];
-  if (!inverse) {
-    v[5] = make_double2(r * (t5.x + t5.y), r * (t5.y - t5.x));    // (1 - i)/sqrt2
-    v[7] = make_double2(r * (t7.y - t7.x), -r * (t7.x + t7.y));   // (-1 - i)/sqrt2
-  } else {
-    v[5] = make_double2(r * (t5.x - t5.y), r * (t5.x + t5.y));    // (1 + i)/sqrt2
-    v[7] = make_double2(-r * (t7.x + t7.y), r * (t7.x - t7.y));   // (-1 + i)/sqrt2
-  }
-  v[6] = sk_muli(v[6], inverse);
-  sk_fft4(v[0], v[1], v[2], v[3], inverse);
-  sk_fft4(v[4], v[5], v[6], v[7], inverse);
-  // interleave: X[2m] = even[m], X[2m+1] = odd[m]
-  double2 e1 = v[1], e2 = v[2], e3 = v[3], o0 = v[4], o1 = v[5], o2 = v[6];
-  v[1] = o0;
-  v[2] = e1;
-  v[3] = o1;
-  v[4] = e2;
-  v[5] = o2;
-  v[6] = e3;
-  // v[0] = e0, v[7] = o3 stay
-}
-
-template <bool STRIDED>
-__device__ __forceinline__ void dct_fft_sk(double2* s, int M, int logM, int W, int logW, const double2* __restrict__ tw8,
-                                           bool inverse) {
-  const int tid = threadIdx.x;
-  const int MP = DCT_PADDED(M);
-  const int line = STRIDED ? (tid & (W - 1)) : (tid >> (logM - 3));
-  const int q = STRIDED ? (tid >> logW) : (tid & ((M >> 3) - 1));
-  double2* base = STRIDED ? s + line : s + (long long)line * MP;
-  const int es = STRIDED ? W : 1;
-  int logNs = 0, logrem = logM;
-  while (logrem > 0) {
-    const int logR = logrem >= 3 ? 3 : logrem;  // radix 8, then one last pass of radix 4 or 2
-    const int R = 1 << logR, nb = 8 >> logR;    // butterflies per thread
-    const int Ns = 1 << logNs;
-    const int stride = M >> logR;               // input stride between the R points of a butterfly
-    const int tsh = logM - logNs - logR;        // twiddle index = r * k << tsh
-    double2 v[8];
-    int pos[8];
-    // compile-time shaped gathers (dynamic indexing of v[] would push it to local memory)
-#define SK_GATHER(LOGR_)                                                                     \
-    _Pragma("unroll") for (int b = 0; b < (8 >> (LOGR_)); ++b) {                                \
-      const int j = q + b * (M >> 3);                                                         \
-      const int k = j & (Ns - 1);                                                             \
-      _Pragma("unroll") for (int r = 0; r < (1 << (LOGR_)); ++r) {                              \
-        double2 x = base[(long long)dct_pad(j + r * stride) * es];                            \
-        if (r > 0 && logNs > 0) {                                                             \
-          double2 t = __ldg(tw8 + ((r * k) << tsh));                                          \
-          if (inverse) t.y = -t.y;                                                            \
-          x = dct_cmul(t, x);                                                                 \
-        }                                                                                     \
-        v[b * (1 << (LOGR_)) + r] = x;                                                        \
-        pos[b * (1 << (LOGR_)) + r] = ((j >> logNs) << (logNs + (LOGR_))) + k + r * Ns;       \
-      }                                                                                       \
-    }
-    if (logR == 3) {
-      SK_GATHER(3)
-    } else if (logR == 2) {
-      SK_GATHER(2)
-    } else {
-      SK_GATHER(1)
-    }
-#undef SK_GATHER
-    if (logR == 3) {
-      sk_fft8(v, inverse);
-    } else if (logR == 2) {
-      sk_fft4(v[0], v[1], v[2], v[3], inverse);
-      sk_fft4(v[4], v[5], v[6], v[7], inverse);
-    } else {
-      sk_fft2(v[0], v[1]);
-      sk_fft2(v[2], v[3]);
-      sk_fft2(v[4], v[5]);
-      sk_fft2(v[6], v[7]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) base[(long long)dct_pad(pos[i]) * es] = v[i];
-    __syncthreads();
-    logNs += logR;
-    logrem -= logR;
-  }
-}
-
 // shared memory: s[M*W] complex, and for MODE 2 additionally cb[n*W] real
 template <bool STRIDED, int MODE>
 static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__ in, double* __restrict__ out, LineGeom g, int logM,
@@ -241,31 +132,17 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
 
   // ---------------- forward half (MODE 0, 2)
   if (MODE != 1) {
-    // batches of 8 independent global loads per thread (one load latency per batch instead of per element)
-    for (int q0 = threadIdx.x; q0 < n * W; q0 += 8 * blockDim.x) {
-      double xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int q = q0 + u * blockDim.x;
-        const int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
-        const int e = STRIDED ? (q >> logW) : (q & (n - 1));
-        xv[u] = (q < n * W && line < nl) ? __ldg(in + base + line * lstride + (long long)e * g.es) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int q = q0 + u * blockDim.x;
-        if (q < n * W) {
-          const int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
-          const int e = STRIDED ? (q >> logW) : (q & (n - 1));
-          const int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
-          const int p = m >> 1;  // natural order (Stockham FFT)
-          const long long ci = STRIDED ? (long long)dct_pad(p) * W + line : (long long)line * MP + dct_pad(p);
-          sd[2 * ci + (m & 1)] = xv[u];
-        }
-      }
+    for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
+      int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
+      int e = STRIDED ? (q >> logW) : (q & (n - 1));
+      double xv = (line < nl) ? in[base + line * lstride + (long long)e * g.es] : 0.0;
+      int m = (e & 1) ? (n - 1 - (e >> 1)) : (e >> 1);
+      int p = dct_bitrev(m >> 1, logM);
+      long long ci = STRIDED ? (long long)dct_pad(p) * W + line : (long long)line * MP + dct_pad(p);
+      sd[2 * ci + (m & 1)] = xv;
     }
     __syncthreads();
-    dct_fft_sk<STRIDED>(s, M, logM, W, logW, tb.tw, false);
+    dct_fft<STRIDED>(s, M, logM, W, logW, tb.tw, false);
     for (int q = threadIdx.x; q < (M + 1) * W; q += blockDim.x) {
       // items 0 .. M*W-1 cover k < M (shift/mask indexing); the last W items are k = M of every line
       int line, k;
@@ -306,7 +183,6 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
   }
   // ---------------- inverse half (MODE 1, 2)
   if (MODE != 0) {
-#pragma unroll 4
     for (int q = threadIdx.x; q < M * W; q += blockDim.x) {
       int line = STRIDED ? (q & (W - 1)) : (q >> logM);
       int k = STRIDED ? (q >> logW) : (q & (M - 1));
@@ -317,10 +193,10 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
         double ck, cnk, cj, cnj;
         if (MODE == 1) {
           long long gb = base + line * lstride;
-          ck = __ldg(in + gb + (long long)k * g.es);
-          cnk = k > 0 ? __ldg(in + gb + (long long)(n - k) * g.es) : 0.0;
-          cj = __ldg(in + gb + (long long)j2 * g.es);
-          cnj = __ldg(in + gb + (long long)(n - j2) * g.es);  // j2 >= 1 always (k < M)
+          ck = in[gb + (long long)k * g.es];
+          cnk = k > 0 ? in[gb + (long long)(n - k) * g.es] : 0.0;
+          cj = in[gb + (long long)j2 * g.es];
+          cnj = in[gb + (long long)(n - j2) * g.es];  // j2 >= 1 always (k < M)
         } else {
           ck = cb[(long long)k * W + line];
           cnk = k > 0 ? cb[(long long)(n - k) * W + line] : 0.0;
@@ -334,14 +210,14 @@ static __global__ void __launch_bounds__(1024) k_dct2(const double* __restrict__
         double2 od = dct_cmul(dct_conj(__ldg(tb.wn + k)), make_double2(0.5 * (vk.x - vjc.x), 0.5 * (vk.y - vjc.y)));
         z = make_double2(ev.x - od.y, ev.y + od.x);  // Ev + i Od
       }
-      int p = k;  // natural order (Stockham FFT)
+      int p = dct_bitrev(k, logM);
       if (STRIDED)
         s[(long long)dct_pad(p) * W + line] = z;
       else
         s[(long long)line * MP + dct_pad(p)] = z;
     }
     __syncthreads();
-    dct_fft_sk<STRIDED>(s, M, logM, W, logW, tb.tw, true);
+    dct_fft<STRIDED>(s, M, logM, W, logW, tb.tw, true);
     for (int q = threadIdx.x; q < n * W; q += blockDim.x) {
       int line = STRIDED ? (q & (W - 1)) : (q >> (logM + 1));
       int e = STRIDED ? (q >> logW) : (q & (n - 1));

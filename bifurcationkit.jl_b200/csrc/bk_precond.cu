@@ -107,13 +107,13 @@ static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type) {
   pc.pow2[d] = (type == 0 && is_pow2(n)) ? 1 : 0;
   if (pc.pow2[d]) {
     const long long M = n / 2;
-    std::vector<double2> tw(M), wn(M + 1), dtw(M + 1);  // tw: full circle for the Stockham passes
-    for (long long k = 0; k < M; ++k) tw[k] = make_double2((double)cosl(-2.0L * PI * k / M), (double)sinl(-2.0L * PI * k / M));
+    std::vector<double2> tw(M / 2), wn(M + 1), dtw(M + 1);
+    for (long long k = 0; k < M / 2; ++k) tw[k] = make_double2((double)cosl(-2.0L * PI * k / M), (double)sinl(-2.0L * PI * k / M));
     for (long long k = 0; k <= M; ++k) {
       wn[k] = make_double2((double)cosl(-2.0L * PI * k / n), (double)sinl(-2.0L * PI * k / n));
       dtw[k] = make_double2((double)cosl(-PI * k / (2.0L * n)), (double)sinl(-PI * k / (2.0L * n)));
     }
-    BK_TRY(upload(c, (void**)&pc.tw[d], tw.data(), 16 * M));
+    BK_TRY(upload(c, (void**)&pc.tw[d], tw.data(), 16 * (M / 2)));
     BK_TRY(upload(c, (void**)&pc.wn[d], wn.data(), 16 * (M + 1)));
     BK_TRY(upload(c, (void**)&pc.dtw[d], dtw.data(), 16 * (M + 1)));
   } else {
@@ -221,13 +221,12 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
       env_w = a ? atoi(a) : 0;
       env_t = b ? atoi(b) : 0;
     }
-    int W = 4096 / g.n;  // one thread owns 8 complex points: blockDim = (n/2) * W / 8 = 256
+    int W = 4096 / g.n;
     if (W < 1) W = 1;
+    if (W > 16) W = 16;
     if (env_w > 0) W = env_w;
     while (W & (W - 1)) W &= W - 1;  // power of two (shift/mask indexing in the kernels)
-    while ((g.n / 2) * W / 8 > 1024) W >>= 1;
-    const int nthr = (g.n / 2) * W / 8;
-    (void)env_t;
+    const int nthr = env_t > 0 ? env_t : 512;
     const int mode = fused_sym ? 2 : (dir > 0 ? 0 : 1);
     size_t sm = sizeof(double2) * (size_t)DCT_PADDED(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
     int logM = ilog2(g.n / 2);
