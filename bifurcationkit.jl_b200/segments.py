@@ -39,6 +39,43 @@ class SeedGrabber:
         return u0, p0, u1, p1
 
 
+def segment_starts(rank, world, steps, subs=4):
+    """Interleaved partition of a window of world*steps scout steps into world*nsub sub-segments of `sub` steps:
+    rank r owns sub-segments g = s*world + r (s = 0..nsub-1), i.e. every rank samples the whole window, so that hard
+    stretches of the branch (folds of the snaking region: rejected steps) are spread over the ranks.
+    Returns [(scout_step_of_first_seed, nsteps), ...]."""
+    sub = max(1, steps // subs)
+    out, left, s = [], steps, 0
+    while left > 0:
+        k = min(sub, left)
+        out.append(((s * world + rank) * sub, k))
+        left -= k
+        s += 1
+    return out
+
+
+class MultiSeedGrabber:
+    """Scout callback collecting the seed pairs (steps a, a+1) of several sub-segments; stops after the last one."""
+
+    def __init__(self, starts, copy):
+        self.want = sorted(set(a for a, _ in starts) | set(a + 1 for a, _ in starts))
+        self.stop_at = self.want[-1]
+        self.copy, self.seeds, self.last = copy, {}, []
+
+    def __call__(self, st):
+        if st.step in self.want:
+            self.seeds[st.step] = (self.copy(st.z_u), st.z_p)
+        self.last = (self.last + [(st.step, self.copy(st.z_u), st.z_p)])[-2:]
+        return st.step < self.stop_at
+
+    def pair(self, a):
+        if a in self.seeds and a + 1 in self.seeds:
+            (u0, p0), (u1, p1) = self.seeds[a], self.seeds[a + 1]
+            return u0, p0, u1, p1
+        (_, u0, p0), (_, u1, p1) = self.last  # the scout ended early: seed from its last two points
+        return u0, p0, u1, p1
+
+
 def rows_to_array(rows, nrows):
     """Fixed-size (nrows, 4) array for the collective; unused rows are NaN."""
     R = np.full((nrows, len(ROW)), np.nan)
