@@ -43,6 +43,7 @@ def domain(n):
 PAR = (-0.1, 1.3)                            # (l, nu) examples/SH2d-fronts.jl:55
 CONT = dict(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0)  # examples/SH2d-fronts.jl:86
 GMRES = dict(reltol=1e-5, restart=100, maxiter=100)  # examples/SH2d-fronts.jl:122 (reltol), config "GMRES(100)"
+BRANCH = {"kind": "front"}  # "front": localized front of SH2d-fronts.jl:70-80; "hexagons": the example's own continuation (:88-92)
 BLS = {"kind": "matrixfree"}  # MatrixFreeBLS (1 GMRES on the N+1 bordered system) or "bordering" (BorderingBLS: 2 GMRES + BEC)
 
 
@@ -72,7 +73,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -132,6 +133,12 @@ def gpu_setup(bk, n, device, host_state=False):
     prob = P.BifurcationProblemB200(ctx, wrap(sol0(n)), PAR, lens=0)
     hexa = P.newton(prob, prob.u0, PAR[0], opt, P.norminf)
     assert hexa.converged, hexa.residuals
+    if BRANCH["kind"] == "hexagons":
+        # the branch the example itself continues: continuation(prob, PALC(), optcont) with prob.u0 = vec(sol0)
+        # (examples/SH2d-fronts.jl:88-92; the line that would substitute the deflated front is commented out, :87)
+        pol = P.newton(prob, hexa.u, PAR[0], P.NewtonPar(tol=1e-9, max_iterations=30, linsolver=ls), P.norminf)
+        assert pol.converged, pol.residuals
+        return ctx, ls, pol.u
     uh = hexa.u if host_state else hexa.u.numpy()
     prob = P.BifurcationProblemB200(ctx, wrap(front_guess(uh, n)), PAR, lens=0)
     fr = P.newton(prob, prob.u0, PAR[0], P.NewtonPar(tol=1e-9, max_iterations=30, linsolver=ls), P.norminf)
@@ -253,9 +260,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bls", default="matrixfree", choices=["matrixfree", "bordering"])
+    ap.add_argument("--branch", default="front", choices=["front", "hexagons"])
     args = ap.parse_args()
     n = args.grid
     BLS["kind"] = args.bls
+    BRANCH["kind"] = args.branch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

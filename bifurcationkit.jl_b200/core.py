@@ -227,7 +227,7 @@ class Jacobian:
 
 
 def make_opts(reltol=1e-8, abstol=0.0, restart=200, maxiter=100, pc_side=_l.BK_SIDE_NONE, orth=_l.BK_ORTH_CGS, fused=True):
-    return _l.GmresOpts(reltol, abstol, restart, maxiter, pc_side, orth, 1 if fused else 0, 0)
+    return _l.GmresOpts(reltol, abstol, restart, maxiter, pc_side, orth, int(fused), 0)  # fused: 0 off, 1 auto, 2 force
 
 
 class GMRESB200:

@@ -333,8 +333,13 @@ static int launch_fused2(bk_ctx* c, const OpDesc& op, const double* in, const do
 // ------------------------------------------------------------------------------------------------ host
 static inline int chunk_grid(long long n) { return (int)((n + BK_TILE - 1) / BK_TILE); }
 
-static bool fused_available(const OpDesc& op) {
-  return ((op.kind == BK_SH2D || op.kind == BK_SH3D) && !op.bordered) || (op.kind == BK_SH2D && op.bordered && op.nx % 2 == 0);
+// fused_mode: bk_gmres_opts.fused -- 0 never, 1 automatic (the measured-fastest arrangement), 2 wherever a fused kernel exists.
+// 3-D: the fused kernel is still the first-generation one (64 KB tiles, 2.3 waves at 128^3) and measured 17% slower per
+// iteration than stand-alone JVP + TMA-ring dots, so "automatic" keeps it off until a TMA-ring 3-D kernel exists.
+static bool fused_available(const OpDesc& op, int fused_mode = 2) {
+  if (op.kind == BK_SH2D) return !op.bordered || (op.nx % 2 == 0);
+  if (op.kind == BK_SH3D) return !op.bordered && fused_mode >= 2;
+  return false;
 }
 
 static size_t dots_smem(int j) { return sizeof(double) * 8 * (size_t)(j > 0 ? j : 1); }
@@ -451,7 +456,7 @@ static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lon
     BK_TRY(bk_precond_apply_dev(c, in, c->z, n));
     in = c->z;
   }
-  const bool fuse = o->fused && fused_available(op) && !left;
+  const bool fuse = o->fused && fused_available(op, o->fused) && !left;
   TimerScope ts(c);
   const double* wfin = c->w;
   if (fuse) {
@@ -623,7 +628,7 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
       if (cudaEventElapsedTime(&t, c->tpairs[i].first, c->tpairs[i].second) == cudaSuccess) ms += t;
     }
     c->stats.last_fused_ms = ms;
-    if (o->fused && fused_available(op) && !(o->pc_side == BK_SIDE_LEFT && c->pc.kind != BK_PC_NONE)) c->stats.total_fused_ms += ms;
+    if (o->fused && fused_available(op, o->fused) && !(o->pc_side == BK_SIDE_LEFT && c->pc.kind != BK_PC_NONE)) c->stats.total_fused_ms += ms;
   }
   if (converged) *converged = conv ? 1 : 0;
   if (iters) *iters = total;

@@ -60,7 +60,8 @@ typedef struct bk_gmres_opts {
   int32_t maxiter; /* 100  */
   int32_t pc_side; /* BK_SIDE_*: which of Pl / Pr holds the context's preconditioner */
   int32_t orth;    /* BK_ORTH_CGS (single classical Gram-Schmidt pass) or BK_ORTH_CGS2 */
-  int32_t fused;   /* 1: JVP fused into the Arnoldi dot-product kernel where available; 0: separate kernels */
+  int32_t fused;   /* 0: separate kernels; 1: automatic (JVP fused into the Arnoldi dot kernel where that is the fastest
+                      arrangement: 2-D SH incl. the bordered map); 2: fused wherever a fused kernel exists (also 3-D SH) */
   int32_t reserved;
 } bk_gmres_opts;
 

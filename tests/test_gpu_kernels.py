@@ -207,3 +207,24 @@ def test_bls_map_and_bordered_solvers(bk):
         dXd, dld, okd, _ = solver(J, ctx.to_device(a), ctx.to_device(b), dzp, ctx.to_device(R), n, xiu, xip,
                                   shift=shift, dotscale=1.0 / N)
         assert _rel(dXd.numpy(), ref[:N]) < 1e-8 and abs(dld - ref[N]) < 1e-8 * max(1, abs(ref[N]))
+
+
+@pytest.mark.parametrize("fused", [2, 1, 0])
+@pytest.mark.parametrize("side", ["none", "right", "left"])
+def test_gmres_sh3d_fused_and_unfused_paths_agree_with_oracle(bk, fused, side):
+    """3-D: v1 fused stencil kernel vs stand-alone JVP + TMA-ring dots, with the DCT preconditioner on either side."""
+    from oracle import precond as oprecond
+    dims, L = (32, 16, 16), (4 * np.pi, 2 * np.pi, 2 * np.pi)
+    sh = problems.SwiftHohenberg(dims, L, l=0.1, nu=1.2)
+    u = problems.sh3d_sol0(*dims, *L)
+    rhs = np.random.default_rng(31).standard_normal(sh.N)
+    Pinv = oprecond.dct_precond(dims, L, 1.0)
+    kw = {"none": {}, "right": dict(Pr=Pinv), "left": dict(Pl=Pinv)}[side]
+    a0, a1 = 40.0, -1.0  # shifted operator: definite, converges for every variant
+    xo, oko, ito = krylov.GMRESIterativeSolvers(reltol=1e-9, restart=120, maxiter=120, **kw)(lambda v: sh.dF(u, v), rhs, a0=a0, a1=a1)
+    ctx = bk.Context(bk.BK_SH3D, dims, L, krylov_m=120, params=(0.1, 1.2))
+    ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    ls = bk.GMRESB200(reltol=1e-9, restart=120, maxiter=120, fused=fused, Pr=side == "right", Pl=side == "left")
+    x, ok, it = ls(ctx.jacobian(u), rhs, a0=a0, a1=a1)
+    assert ok and oko, (ok, oko, it, ito)
+    assert abs(it - ito) <= 3 and _rel(x, xo) < 1e-7, (it, ito, _rel(x, xo))

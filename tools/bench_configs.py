@@ -80,8 +80,9 @@ if "5" in which:
     s0 = (np.cos(X)[None, None, :] * np.cos(X)[None, :, None] * np.ones(n3)[:, None, None])
     s0 = s0 - s0.min(); s0 = s0 / s0.max() * 1.2
     ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
-    ls = bk.GMRESB200(reltol=1e-9, restart=150, maxiter=150, Pr=True, orth="cgs2")  # rtol of examples/SH3d.jl:93
-    ls_newton = bk.GMRESB200(reltol=1e-4, restart=150, maxiter=150, Pr=True)
+    FUSED = os.environ.get("BK_FUSED3D", "1") == "1"
+    ls = bk.GMRESB200(reltol=1e-9, restart=150, maxiter=150, Pr=True, orth="cgs2", fused=FUSED)  # rtol of examples/SH3d.jl:93
+    ls_newton = bk.GMRESB200(reltol=1e-4, restart=150, maxiter=150, Pr=True, fused=FUSED)
     prob = P.BifurcationProblemB200(ctx, ctx.to_device(s0.reshape(-1)), (0.1, 1.2), lens=0)
     ctx.sync(); t0 = time.perf_counter()
     sol = P.newton(prob, prob.u0, 0.1, P.NewtonPar(tol=1e-8, max_iterations=80, linsolver=ls_newton), P.norminf)

@@ -6,6 +6,7 @@ import bench
 bk = g.load_package(); P = bk.palc
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+bench.BRANCH['kind'] = sys.argv[4] if len(sys.argv) > 4 else 'front'
 ctx, ls, u_front = bench.gpu_setup(bk, n, 0)
 cp = P.ContinuationPar(max_steps=steps, newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls), **bench.CONT)
 prob = P.BifurcationProblemB200(ctx, u_front, bench.PAR, lens=0)
