@@ -121,17 +121,20 @@ def test_gmres_sh2d_vs_oracle(bk, fused, orth):
     J = ctx.jacobian(u)
     ols = krylov.GMRESIterativeSolvers(reltol=1e-10, restart=80, maxiter=80)
     ls = bk.GMRESB200(reltol=1e-10, restart=80, maxiter=80, orth=orth, fused=fused)
-    for a0, a1 in ((3.0, -1.0), (0.0, 1.0)):
+    for a0, a1 in ((3000.0, -1.0), (0.0, 1.0)):  # (3000 I - J): condition number ~4; J alone: not solvable in 80 its
         xo, oko, ito = ols(lambda v: sh.dF(u, v), rhs, a0=a0, a1=a1)
         x, ok, it = ls(J, rhs, a0=a0, a1=a1)
         assert ok == oko
+        assert oko == (a0 != 0.0)
         if oko:
             assert abs(it - ito) <= 2, (it, ito)
             assert _rel(x, xo) < 1e-8
             # true residual
             A = a0 * np.eye(1)[0, 0]
             r = rhs - (a0 * x + a1 * sh.dF(u, x))
-            assert np.linalg.norm(r) <= 2e-10 * np.linalg.norm(rhs) * 5
+            assert np.linalg.norm(r) <= 1e-9 * np.linalg.norm(rhs)
+        else:
+            assert it == 80  # maxiter reached, never throws
         # device-resident rhs
         xd, okd, itd = ls(J, ctx.to_device(rhs), a0=a0, a1=a1)
         assert itd == it and np.array_equal(xd.numpy(), x)

@@ -82,7 +82,7 @@ if "5" in which:
     ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
     FUSED = os.environ.get("BK_FUSED3D", "1") == "1"
     ls = bk.GMRESB200(reltol=1e-9, restart=150, maxiter=150, Pr=True, orth="cgs2", fused=FUSED)  # rtol of examples/SH3d.jl:93
-    ls_newton = bk.GMRESB200(reltol=1e-4, restart=150, maxiter=150, Pr=True, fused=FUSED)
+    ls_newton = bk.GMRESB200(reltol=1e-6, restart=150, maxiter=150, Pr=True, fused=FUSED)
     prob = P.BifurcationProblemB200(ctx, ctx.to_device(s0.reshape(-1)), (0.1, 1.2), lens=0)
     ctx.sync(); t0 = time.perf_counter()
     sol = P.newton(prob, prob.u0, 0.1, P.NewtonPar(tol=1e-8, max_iterations=80, linsolver=ls_newton), P.norminf)
