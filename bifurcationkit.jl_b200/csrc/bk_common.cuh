@@ -45,6 +45,10 @@ struct Precond {
   double* work2 = nullptr;
   // chan tridiagonal LU factors
   double* tri = nullptr;
+  // potrap circulant preconditioner
+  void* blas = nullptr;      // cublasHandle_t
+  double2* tdft = nullptr;   // exp(-2 pi i j / (M-1))
+  double po_r = 0, po_nu = 0, po_T = 0;
 };
 
 struct bk_ctx {

@@ -148,6 +148,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
     if (c->pc.lam[d]) cudaFree(c->pc.lam[d]);
     if (c->pc.dense[d]) cudaFree(c->pc.dense[d]);
   }
+  if (c->pc.tdft) cudaFree(c->pc.tdft);
   if (c->counters) cudaFree(c->counters);
   for (auto& kv : c->vec_live) cudaFree(kv.first);
   for (double* b : c->stage)

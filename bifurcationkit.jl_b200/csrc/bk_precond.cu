@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <utility>
 #include <vector>
+#include <cublas_v2.h>
 #include "bk_common.cuh"
 
 #include "bk_dct.cuh"
@@ -59,6 +60,72 @@ static __global__ void __launch_bounds__(256) k_helmholtz_symbol_div(double* __r
     int i = (int)(g % nx), j = (int)(g / nx);
     a[q] = a[q] / (a0 + a1 * (lx[i] + ly[j]));
   }
+}
+
+// ---- potrap circulant preconditioner: time direction -------------------------------------------------------------------
+// B holds the DST-I coefficients of all 2M slice components (field f = 2*slice + comp, n values each).  One thread per
+// spatial mode: w+- = u1 +- i u2 over the K = M-1 cyclic slices, DFT in time, divide by
+//   s+-_k = (1 - g_k) - h/2 (1 + g_k)(lambda + r +- i nu),   g_k = exp(-2 pi i k/K),
+// inverse DFT, back to (u1, u2).  In place.
+#define BK_PO_KMAX 64
+static __global__ void __launch_bounds__(128) k_potrap_time(double* __restrict__ B, long long n, int nx, int K,
+                                                            const double* __restrict__ lamx, const double* __restrict__ lamy,
+                                                            double h, double r, double nu, const double2* __restrict__ tw) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const double lam = lamx[g % nx] + lamy[g / nx];
+  double2 wp[BK_PO_KMAX], wm[BK_PO_KMAX];
+  for (int i = 0; i < K; ++i) {
+    const double a = B[(long long)(2 * i) * n + g], b = B[(long long)(2 * i + 1) * n + g];
+    wp[i] = make_double2(a, b);
+    wm[i] = make_double2(a, -b);
+  }
+  double2 yp[BK_PO_KMAX], ym[BK_PO_KMAX];
+  const double invK = 1.0 / K;
+  for (int k = 0; k < K; ++k) {
+    double2 ap = make_double2(0, 0), am = make_double2(0, 0);
+    int idx = 0;
+    for (int i = 0; i < K; ++i) {
+      const double2 t = tw[idx];  // exp(-2 pi i k i / K)
+      ap.x += wp[i].x * t.x - wp[i].y * t.y;
+      ap.y += wp[i].x * t.y + wp[i].y * t.x;
+      am.x += wm[i].x * t.x - wm[i].y * t.y;
+      am.y += wm[i].x * t.y + wm[i].y * t.x;
+      idx += k;
+      if (idx >= K) idx -= K;
+    }
+    const double2 gk = tw[k];
+    // s = (1 - g) - h/2 (1 + g) (lam + r +- i nu)
+    const double2 omg = make_double2(1.0 - gk.x, -gk.y), opg = make_double2(1.0 + gk.x, gk.y);
+    const double cr = lam + r;
+    double2 sp = make_double2(omg.x - 0.5 * h * (opg.x * cr - opg.y * nu), omg.y - 0.5 * h * (opg.x * nu + opg.y * cr));
+    double2 sm = make_double2(omg.x - 0.5 * h * (opg.x * cr + opg.y * nu), omg.y - 0.5 * h * (-opg.x * nu + opg.y * cr));
+    const double dp = 1.0 / (sp.x * sp.x + sp.y * sp.y), dm = 1.0 / (sm.x * sm.x + sm.y * sm.y);
+    yp[k] = make_double2((ap.x * sp.x + ap.y * sp.y) * dp * invK, (ap.y * sp.x - ap.x * sp.y) * dp * invK);
+    ym[k] = make_double2((am.x * sm.x + am.y * sm.y) * dm * invK, (am.y * sm.x - am.x * sm.y) * dm * invK);
+  }
+  for (int i = 0; i < K; ++i) {
+    double2 ap = make_double2(0, 0), am = make_double2(0, 0);
+    int idx = 0;
+    for (int k = 0; k < K; ++k) {
+      const double2 t = tw[idx];  // conj -> exp(+2 pi i k i / K)
+      ap.x += yp[k].x * t.x + yp[k].y * t.y;
+      ap.y += yp[k].y * t.x - yp[k].x * t.y;
+      am.x += ym[k].x * t.x + ym[k].y * t.y;
+      am.y += ym[k].y * t.x - ym[k].x * t.y;
+      idx += i;
+      if (idx >= K) idx -= K;
+    }
+    B[(long long)(2 * i) * n + g] = 0.5 * (ap.x + am.x);      // Re((yp + ym)/2)
+    B[(long long)(2 * i + 1) * n + g] = 0.5 * (ap.y - am.y);  // Re((yp - ym)/(2i)) = Im(yp - ym)/2
+  }
+}
+// closure row of the preconditioner: x_M = r_M + x_1; the period entry passes through
+static __global__ void __launch_bounds__(256) k_potrap_close(const double* __restrict__ in, double* __restrict__ out,
+                                                             long long Ns, int M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Ns) out[(long long)(M - 1) * Ns + i] = in[(long long)(M - 1) * Ns + i] + out[i];
+  if (i == 0) out[(long long)M * Ns] = in[(long long)M * Ns];
 }
 
 // Thomas solve with precomputed factors: tri = [cprime (n) | denom_inv (n) | lower (n)]
@@ -159,6 +226,28 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
       double h = 2 * c->lengths[d] / c->dims[d];
       BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1));
     }
+  } else if (kind == BK_PC_POTRAP_CIRC) {
+    BK_CHECK(c, c->kind == BK_POTRAP_CGL2D, "BK_PC_POTRAP_CIRC needs a Trapeze (potrap) context");
+    const int K = (int)c->dims[2] - 1;
+    BK_CHECK(c, K >= 1 && K <= BK_PO_KMAX, "BK_PC_POTRAP_CIRC supports 2 <= M <= 65 time slices");
+    BK_CHECK(c, a0 > 0, "BK_PC_POTRAP_CIRC: a0 must be the period T > 0");
+    for (int d = 0; d < 2; ++d) {
+      double h = 2 * c->lengths[d] / c->dims[d];
+      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1));
+    }
+    std::vector<double2> tw(K);
+    const long double PI = 3.14159265358979323846264338327950288L;
+    for (int j = 0; j < K; ++j) tw[j] = make_double2((double)cosl(-2.0L * PI * j / K), (double)sinl(-2.0L * PI * j / K));
+    BK_TRY(upload(c, (void**)&pc.tdft, tw.data(), 16 * (size_t)K));
+    if (!pc.blas) {
+      cublasHandle_t hnd;
+      BK_CHECK(c, cublasCreate(&hnd) == CUBLAS_STATUS_SUCCESS, "cublasCreate failed");
+      cublasSetStream(hnd, c->stream);
+      pc.blas = (void*)hnd;
+    }
+    pc.po_T = a0;
+    pc.po_r = c->par[0];   // (r, mu, nu, c3, c5)
+    pc.po_nu = c->par[2];
   } else if (kind == BK_PC_CHAN_TRIDIAG) {
     BK_CHECK(c, c->kind == BK_CHAN, "BK_PC_CHAN_TRIDIAG needs a chan context");
     long long n = c->N;
@@ -340,6 +429,32 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
     BK_TRY(transform_pass(c, 1, -1, B, A, nx, ny, (int)nblk));
     BK_TRY(transform_pass(c, 0, -1, A, out, nx, ny, (int)nblk));
     if (c->kind == BK_POTRAP_CGL2D) BK_CUDA(c, cudaMemcpyAsync(out + N - 1, in + N - 1, 8, cudaMemcpyDeviceToDevice, c->stream));
+  } else if (pc.kind == BK_PC_POTRAP_CIRC) {
+    const int nx = (int)c->dims[0], ny = (int)c->dims[1], M = (int)c->dims[2];
+    const long long nn = (long long)nx * ny, Ns = 2 * nn;
+    const int nf = 2 * M;
+    cublasHandle_t hnd = (cublasHandle_t)pc.blas;
+    const double one = 1.0, zero = 0.0;
+    double* A = pc.work;
+    double* Bf = pc.work2;
+    const double* Sx = pc.dense[0];
+    const double* Sy = pc.dense[1];
+    // DST-I in space as dense GEMMs (the DST-I of 512 points needs a 1026-point FFT; fp64 GEMM is ~2 ms at 512^2 x 60):
+    // column-major view of a field = nx x ny;  A = Sx * in (all fields at once),  B_f = A_f * Sy (batched)
+    BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, in, nx, &zero, A, nx) ==
+                    CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
+    BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, A, nx, nn, Sy, ny, 0, &zero, Bf, nx, nn,
+                                          nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
+    k_potrap_time<<<(unsigned)((nn + 127) / 128), 128, 0, c->stream>>>(Bf, nn, nx, M - 1, pc.lam[0], pc.lam[1], pc.po_T / M,
+                                                                    pc.po_r, pc.po_nu, pc.tdft);
+    BK_CUDA(c, cudaGetLastError());
+    BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, Bf, nx, nn, Sy, ny, 0, &zero, A, nx, nn,
+                                          nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
+    BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, A, nx, &zero, out, nx) ==
+                    CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
+    k_potrap_close<<<(unsigned)((Ns + 255) / 256), 256, 0, c->stream>>>(in, out, Ns, M);
+    c->stats.kernel_launches += 6;
+    BK_CUDA(c, cudaGetLastError());
   } else if (pc.kind == BK_PC_CHAN_TRIDIAG) {
     k_thomas<<<1, 32, 0, c->stream>>>(pc.tri, in, out, (int)N);
     c->stats.kernel_launches++;

@@ -47,7 +47,10 @@ enum {
   BK_PC_NONE = 0,
   BK_PC_SH_DCT = 1,     /* (L1 + shift I)^-1 by separable DCT-II (exact for the Neumann-closure operator) */
   BK_PC_CHAN_TRIDIAG = 2, /* lu(P), P = tridiagonal Laplacian with identity boundary rows (chan.jl:108-109) */
-  BK_PC_CGL_DST = 3     /* per-component (a0 I + a1 Lap_dirichlet)^-1 by DST-I (stand-in for cGL2d.jl:209-213 ILU) */
+  BK_PC_CGL_DST = 3,    /* per-component (a0 I + a1 Lap_dirichlet)^-1 by DST-I (block Jacobi over slices) */
+  BK_PC_POTRAP_CIRC = 4 /* Trapeze PO Jacobian of cGL linearised at the trivial state: DST-I in space (dense, cuBLAS DGEMM),
+                           u1 +- i u2, DFT over the M-1 cyclic slices, scalar symbol; a0 = period T.  Stand-in for the ILU
+                           of the assembled PO Jacobian (examples/cGL2d.jl:209-213) */
 };
 enum { BK_SIDE_NONE = 0, BK_SIDE_LEFT = 1, BK_SIDE_RIGHT = 2 };
 enum { BK_ORTH_CGS = 0, BK_ORTH_CGS2 = 1 };

@@ -72,3 +72,38 @@ def dst_helmholtz_precond(Nx, Ny, lx, ly, a0, a1, workers=1):
         return sfft.idstn(R, type=1, norm="ortho", workers=workers).reshape(-1)
 
     return apply
+
+
+def potrap_circulant_precond(Nx, Ny, lx, ly, M, T, r, nu, workers=1):
+    """Preconditioner for the Trapeze periodic-orbit Jacobian of cGL (stand-in for the ILU of the assembled sparse PO
+    Jacobian, examples/cGL2d.jl:209-213): the PO Jacobian linearised at the trivial state,
+        rows i = 1..M-1:  A x_i - B x_{i-1},  A = I - h/2 J0, B = I + h/2 J0, x_0 == x_{M-1};   row M: x_M - x_1,
+    J0 = Lap_dirichlet + r + nu*R, is block-circulant in time and diagonal in the DST-I basis, so it is inverted exactly by
+    DST-I in space, the change of variables u1 +- i u2 (diagonalises R), a length-(M-1) DFT in time and a scalar division.
+    Identity on the period unknown (and on a PALC border entry if present)."""
+    n, Ns, K = Nx * Ny, 2 * Nx * Ny, M - 1
+    hx, hy = 2 * lx / Nx, 2 * ly / Ny
+    lam = dirichlet_eigs(Nx, hx)[None, :] + dirichlet_eigs(Ny, hy)[:, None]
+    h = T / M
+    gam = np.exp(-2j * np.pi * np.arange(K) / K)
+    sp = (1 - gam)[:, None, None] - (h / 2) * (1 + gam)[:, None, None] * (lam[None] + r + 1j * nu)
+    sm = (1 - gam)[:, None, None] - (h / 2) * (1 + gam)[:, None, None] * (lam[None] + r - 1j * nu)
+    NM = Ns * M
+
+    def apply(v):
+        out = np.array(v, dtype=float)
+        X = v[:NM].reshape(M, 2, Ny, Nx)
+        W = sfft.dstn(X[:K], type=1, norm="ortho", axes=(-2, -1), workers=workers)
+        wp, wm = W[:, 0] + 1j * W[:, 1], W[:, 0] - 1j * W[:, 1]
+        yp = np.fft.ifft(np.fft.fft(wp, axis=0) / sp, axis=0)
+        ym = np.fft.ifft(np.fft.fft(wm, axis=0) / sm, axis=0)
+        Y = np.empty_like(W)
+        Y[:, 0] = ((yp + ym) / 2).real
+        Y[:, 1] = ((yp - ym) / 2j).real
+        Z = sfft.idstn(Y, type=1, norm="ortho", axes=(-2, -1), workers=workers)
+        O = out[:NM].reshape(M, 2, Ny, Nx)
+        O[:K] = Z
+        O[M - 1] = X[M - 1] + Z[0]
+        return out  # entries beyond NM (period, border) pass through
+
+    return apply

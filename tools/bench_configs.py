@@ -56,10 +56,9 @@ if "4" in which:
     dx = ctx.to_device(np.random.default_rng(0).standard_normal(N)); out = ctx.zeros()
     J = ctx.jacobian(x)
     t_res = ev_time(ctx, lambda: ctx.residual(x, out)); t_jvp = ev_time(ctx, lambda: ctx.jvp(dx, out))
-    h = 2 * np.pi / M
-    ctx.precond_setup(bk.BK_PC_CGL_DST, 1.0, -h / 2)   # block-Jacobi over slices: (I - h/2 Lap)^-1 by DST
+    ctx.precond_setup(bk.BK_PC_POTRAP_CIRC, 2 * np.pi)  # time-circulant / DST preconditioner (stand-in for the example's ILU)
     t_pc = ev_time(ctx, lambda: ctx.precond_apply(dx, out), reps=5, warm=1)
-    ls = bk.GMRESB200(reltol=1e-3, restart=40, maxiter=50, Pr=True)  # examples/cGL2d.jl:213 settings
+    ls = bk.GMRESB200(reltol=1e-3, restart=40, maxiter=50, Pr=True)  # examples/cGL2d.jl:213 settings (reltol 1e-3, restart 40, maxiter 50)
     rhs = ctx.residual(x)
     bls = bk.MatrixFreeBLSB200(ls)
     tau = ctx.to_device(np.random.default_rng(2).standard_normal(N)); dR = ctx.to_device(np.random.default_rng(3).standard_normal(N))
