@@ -37,16 +37,17 @@ if "1" in which:
         del ctx
 
 if "4" in which:
-    nx = ny = 512; M = 30
+    nx = ny = int(os.environ.get("BK_CGL_N", "512")); M = 30
     L = (np.pi, np.pi / 2)
     n = nx * ny
     hx, hy = 2 * L[0] / nx, 2 * L[1] / ny
     lam1 = -(2 - 2 * np.cos(np.pi / (nx + 1))) / hx**2 - (2 - 2 * np.cos(np.pi / (ny + 1))) / hy**2
-    r = -lam1 + 0.05  # slightly past the Hopf point of the trivial state (r_hopf = -lambda_1)
-    ctx = bk.Context(bk.BK_POTRAP_CGL2D, (nx, ny, M), L, krylov_m=50, params=(r, 0.1, 1.0, -1.0, 1.0))
+    r = -lam1 - 0.01  # r_hopf - 0.01 as examples/cGL2d.jl:177 (r_hopf = -lambda_1(Lap), analytic: SURVEY 8d)
+    pars = (r, 0.1, 1.0, -1.0, 1.0)
+    ctx = bk.Context(bk.BK_POTRAP_CGL2D, (nx, ny, M), L, krylov_m=60, params=pars)
     i = np.arange(1, nx + 1); j = np.arange(1, ny + 1)
     phi11 = (np.sin(np.pi * i / (nx + 1))[None, :] * np.sin(np.pi * j / (ny + 1))[:, None]).reshape(-1)
-    amp = 0.3
+    amp = 1.0  # orbit guess x_k = a phi11 [cos t_k; sin t_k], T = 2 pi (cf. cGL2d.jl:171-174)
     xs = np.concatenate([np.concatenate([amp * phi11 * np.cos(2 * np.pi * k / M), amp * phi11 * np.sin(2 * np.pi * k / M)]) for k in range(M)] + [np.array([2 * np.pi])])
     N = ctx.N
     x = ctx.to_device(xs)
@@ -58,16 +59,34 @@ if "4" in which:
     t_res = ev_time(ctx, lambda: ctx.residual(x, out)); t_jvp = ev_time(ctx, lambda: ctx.jvp(dx, out))
     ctx.precond_setup(bk.BK_PC_POTRAP_CIRC, 2 * np.pi)  # time-circulant / DST preconditioner (stand-in for the example's ILU)
     t_pc = ev_time(ctx, lambda: ctx.precond_apply(dx, out), reps=5, warm=1)
-    ls = bk.GMRESB200(reltol=1e-3, restart=40, maxiter=50, Pr=True)  # examples/cGL2d.jl:213 settings (reltol 1e-3, restart 40, maxiter 50)
-    rhs = ctx.residual(x)
-    bls = bk.MatrixFreeBLSB200(ls)
-    tau = ctx.to_device(np.random.default_rng(2).standard_normal(N)); dR = ctx.to_device(np.random.default_rng(3).standard_normal(N))
+    ls = bk.GMRESB200(reltol=1e-3, restart=40, maxiter=50, Pr=True)  # examples/cGL2d.jl:213: reltol 1e-3, restart 40, maxiter 50
+    prob = P.BifurcationProblemB200(ctx, x, pars, lens=0)
     ctx.sync(); t0 = time.perf_counter()
-    dX, dl, ok, it = bls(J, dR, tau, 0.7, rhs, 0.1, 0.5, 0.5, dotscale=1.0 / N)
+    po = P.newton(prob, x, r, P.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ls), P.norminf)
+    ctx.sync(); t_newton = time.perf_counter() - t0
+    upo = po.u.numpy()
+    # one bordered matrix-free solve at the orbit (the PALC corrector's linear system)
+    Jpo = ctx.jacobian(po.u)
+    rhs = ctx.to_device(np.random.default_rng(1).standard_normal(N))
+    tau = ctx.to_device(np.random.default_rng(2).standard_normal(N)); dR = ctx.to_device(np.random.default_rng(3).standard_normal(N))
+    bls = bk.MatrixFreeBLSB200(ls)
+    bls(Jpo, dR, tau, 0.7, rhs, 0.1, 0.5, 0.5, dotscale=1.0 / N)
+    ctx.sync(); t0 = time.perf_counter()
+    dX, dl, ok, it = bls(Jpo, dR, tau, 0.7, rhs, 0.1, 0.5, 0.5, dotscale=1.0 / N)
     ctx.sync(); t_solve = time.perf_counter() - t0
-    print(json.dumps({"config": f"cGL2d {nx}^2 Trapeze M={M} (N={N}), bordered matrix-free solve", "po_residual_ms": t_res, "po_jvp_ms": t_jvp,
-                      "po_jvp_GBps": 24 * N / 1e6 / t_jvp, "precond_ms": t_pc, "bordered_mf_solve_s": t_solve, "gmres_iters": it, "converged": ok,
-                      "s_per_gmres_iter": t_solve / max(1, it)}), flush=True)
+    # continuation of the periodic orbit in r: PALC + MatrixFreeBLS (continuation_po with linear_algo = MatrixFreeBLS(ls))
+    prob2 = P.BifurcationProblemB200(ctx, po.u, pars, lens=0, record=lambda v: v.norminf())
+    cp = P.ContinuationPar(dsmin=1e-4, dsmax=0.03, ds=0.001, p_min=r - 1.0, p_max=2.5, max_steps=8,   # cGL2d.jl:197 opts_po_cont
+                           newton_options=P.NewtonPar(tol=1e-8, max_iterations=15, linsolver=ls))
+    ctx.sync(); t0 = time.perf_counter()
+    rows, st = P.continuation(prob2, P.PALC(bls=bls), cp, normC=P.norminf)
+    ctx.sync(); t_cont = time.perf_counter() - t0
+    print(json.dumps({"config": f"cGL2d {nx}^2 Trapeze M={M} (N={N}), matrix-free Newton + bordered MF solve, circulant/DST preconditioner",
+                      "po_residual_ms": t_res, "po_jvp_ms": t_jvp, "po_jvp_GBps": 24 * N / 1e6 / t_jvp, "precond_ms": t_pc,
+                      "po_newton": {"converged": po.converged, "its": po.itnewton, "linear_its": po.itlineartot, "seconds": t_newton,
+                                    "period_T": float(upo[-1]), "max_abs_u": float(np.max(np.abs(upo[:-1])))},
+                      "bordered_mf_solve_s": t_solve, "gmres_iters": it, "converged": ok,
+                      "po_continuation": {"steps": len(rows) - 1, "seconds": t_cont, "rows": [[round(q["param"], 6), round(q["x"], 6), q["itnewton"], q["itlinear"]] for q in rows]}}), flush=True)
     del ctx, x, dx, out, rhs, tau, dR
 
 if "5" in which:
