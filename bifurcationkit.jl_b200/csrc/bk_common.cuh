@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -178,7 +179,9 @@ static inline cudaError_t bk_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  static int no_pdl = -1;  // BK_NO_PDL=1: plain stream order (diagnostics)
+  if (no_pdl < 0) no_pdl = getenv("BK_NO_PDL") ? 1 : 0;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 // first statement of every kernel launched through bk_launch_pdl: wait for the previous grid's memory, then let the next

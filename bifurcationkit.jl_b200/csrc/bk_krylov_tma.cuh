@@ -59,6 +59,16 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Executed by every consumer lane between its last ld.shared of a ring stage and the warp's arrive on the stage's
+// `empty` barrier.  The refill of the stage is a TMA (async-proxy) write; without a cross-proxy fence the arrive can
+// become visible while the warp's last ld.shared are still in flight (ptxas schedules the dependent DFMAs *after*
+// SYNCS.ARRIVE), and the refill then overwrites rows that have not been read yet.  Seen as a handful of wrong tiles per
+// launch with E = 8 and several waves of CTAs (tools/k2check); mbarrier release/acquire alone does not order the proxies.
+#ifndef BK2_NO_WAR_FENCE
+__device__ __forceinline__ void consumer_release_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#else
+__device__ __forceinline__ void consumer_release_fence() {}
+#endif
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 #define BK2_MAXSTAGES 8
@@ -129,6 +139,7 @@ __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __re
             if (e < tl.rows && t < lim) a1 = fma(st1[e * BK2_ROW], val[e], a1);
           }
         }
+        consumer_release_fence();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&rg->empty[s0]);
@@ -155,6 +166,7 @@ __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __re
           const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
           if (e < tl.rows && t < lim) val[e] = fma(-g, st[e * BK2_ROW], val[e]);
         }
+        consumer_release_fence();
         __syncwarp();
         if (lane == 0) mbar_arrive(&rg->empty[s]);
       }

@@ -231,3 +231,25 @@ def test_gmres_sh3d_fused_and_unfused_paths_agree_with_oracle(bk, fused, side):
     x, ok, it = ls(ctx.jacobian(u), rhs, a0=a0, a1=a1)
     assert ok and oko, (ok, oko, it, ito)
     assert abs(it - ito) <= 3 and _rel(x, xo) < 1e-7, (it, ito, _rel(x, xo))
+
+
+@pytest.mark.parametrize("N", [4849664, 4849664 + 1, 2424832 + 777])
+def test_gmres_many_waves_of_tall_tiles(bk, N):
+    """Regression: vectors long enough that the TMA-ring kernels run several waves of 8-row tiles (18944 rows of 256 =
+    4 waves of 592 CTAs).  Before the consumers fenced their shared-memory reads against the async-proxy refill of a ring
+    stage, a few tiles per launch were overwritten while still being read: GMRES stalled at ~0.17 and its recursive
+    residual estimate disagreed with the true residual (tools/k2check/k2_check.cu isolates the kernels)."""
+    ctx = bk.Context(bk.BK_CHAN, (N,), (1.0,), krylov_m=40, params=(3.3, 0.01))
+    rng = np.random.default_rng(1)
+    u = 0.1 * rng.standard_normal(N)
+    b = rng.standard_normal(N)
+    J = ctx.jacobian(ctx.to_device(u))
+    rhs = ctx.to_device(b)
+    a0 = -0.4 * float(N - 1) ** 2  # a0 I + J: moderately conditioned, ~34 iterations to 1e-9
+    for orth in ("cgs", "cgs2"):
+        ls = bk.GMRESB200(reltol=1e-9, restart=40, maxiter=40, orth=orth)
+        x, ok, it = ls(J, rhs, a0=a0)
+        true = np.linalg.norm(ctx.jvp(x, a0=a0).numpy() - b) / np.linalg.norm(b)
+        est = ls.last_resnorm / np.linalg.norm(b)
+        assert ok and it <= 38, (orth, it, est, true)
+        assert true < 2e-9 and abs(true - est) < 1e-3 * est + 1e-12, (orth, est, true)

@@ -59,10 +59,12 @@ if "4" in which:
     t_res = ev_time(ctx, lambda: ctx.residual(x, out)); t_jvp = ev_time(ctx, lambda: ctx.jvp(dx, out))
     ctx.precond_setup(bk.BK_PC_POTRAP_CIRC, 2 * np.pi)  # time-circulant / DST preconditioner (stand-in for the example's ILU)
     t_pc = ev_time(ctx, lambda: ctx.precond_apply(dx, out), reps=5, warm=1)
-    ls = bk.GMRESB200(reltol=1e-3, restart=40, maxiter=50, Pr=True)  # examples/cGL2d.jl:213: reltol 1e-3, restart 40, maxiter 50
+    ls = bk.GMRESB200(reltol=float(os.environ.get("BK_PO_RELTOL", "1e-3")), restart=40, maxiter=50, Pr=True,
+                      orth=os.environ.get("BK_PO_ORTH", "cgs2"))  # examples/cGL2d.jl:213: reltol 1e-3, restart 40, maxiter 50
     prob = P.BifurcationProblemB200(ctx, x, pars, lens=0)
     ctx.sync(); t0 = time.perf_counter()
-    po = P.newton(prob, x, r, P.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ls), P.norminf)
+    NT = float(os.environ.get('BK_PO_NEWTON_TOL', '1e-8' if nx <= 256 else '1e-6'))
+    po = P.newton(prob, x, r, P.NewtonPar(tol=NT, max_iterations=20, linsolver=ls), P.norminf)
     ctx.sync(); t_newton = time.perf_counter() - t0
     upo = po.u.numpy()
     # one bordered matrix-free solve at the orbit (the PALC corrector's linear system)
@@ -77,9 +79,14 @@ if "4" in which:
     # continuation of the periodic orbit in r: PALC + MatrixFreeBLS (continuation_po with linear_algo = MatrixFreeBLS(ls))
     prob2 = P.BifurcationProblemB200(ctx, po.u, pars, lens=0, record=lambda v: v.norminf())
     cp = P.ContinuationPar(dsmin=1e-4, dsmax=0.03, ds=0.001, p_min=r - 1.0, p_max=2.5, max_steps=8,   # cGL2d.jl:197 opts_po_cont
-                           newton_options=P.NewtonPar(tol=1e-8, max_iterations=15, linsolver=ls))
+                           newton_options=P.NewtonPar(tol=NT, max_iterations=15, linsolver=ls))
+    print(json.dumps({"po_newton_residuals": po.residuals, "converged": po.converged, "linear_its": po.itlineartot}), flush=True)
     ctx.sync(); t0 = time.perf_counter()
-    rows, st = P.continuation(prob2, P.PALC(bls=bls), cp, normC=P.norminf)
+    try:
+        rows, st = P.continuation(prob2, P.PALC(bls=bls), cp, normC=P.norminf)
+    except RuntimeError as e:
+        print("continuation failed:", str(e)[:300], flush=True)
+        rows = []
     ctx.sync(); t_cont = time.perf_counter() - t0
     print(json.dumps({"config": f"cGL2d {nx}^2 Trapeze M={M} (N={N}), matrix-free Newton + bordered MF solve, circulant/DST preconditioner",
                       "po_residual_ms": t_res, "po_jvp_ms": t_jvp, "po_jvp_GBps": 24 * N / 1e6 / t_jvp, "precond_ms": t_pc,
