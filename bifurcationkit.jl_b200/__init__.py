@@ -13,3 +13,4 @@ from .core import (Context, DeviceVec, Jacobian, GMRESB200, BorderingBLSB200, Ma
                    bls_map, make_opts, hessenberg_eig)
 from . import palc
 from . import segments
+from . import floquet

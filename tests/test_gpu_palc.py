@@ -256,3 +256,53 @@ def test_potrap_circulant_preconditioner(bk):
     A = np.zeros((N + 1, N + 1)); A[:N, :N] = Jd; A[:N, N] = dR; A[N, :N] = 0.5 * tau / N; A[N, N] = 0.5 * 0.7
     ref = np.linalg.solve(A, np.concatenate([rhs, [0.1]]))
     assert okb and _rel(dX, ref[:N]) < 1e-5 and abs(dl - ref[N]) < 1e-5 * max(1.0, abs(ref[N]))
+
+
+def test_cgl_dst_helmholtz_preconditioner(bk):
+    """BK_PC_CGL_DST on the cGL vector field: per-component (a0 I + a1 Lap_dirichlet)^-1, exact by DST-I."""
+    nx, ny = 24, 17
+    ctx = bk.Context(bk.BK_CGL2D, (nx, ny), (np.pi, np.pi / 2), krylov_m=4, params=(1.3, 0.1, 1.0, -1.0, 1.0))
+    n = nx * ny
+    v = np.random.default_rng(2).standard_normal(2 * n)
+    for a0, a1 in ((1.0, 1.0 * -0.3), (0.584, -0.32)):
+        ctx.precond_setup(bk.BK_PC_CGL_DST, a0, a1)
+        P1 = oprecond.dst_helmholtz_precond(nx, ny, np.pi, np.pi / 2, a0, a1)
+        ref = np.concatenate([P1(v[:n]), P1(v[n:])])
+        assert _rel(ctx.precond_apply(v), ref) < 1e-11
+        assert _rel(ctx.precond_apply(ctx.to_device(v)).numpy(), ref) < 1e-11
+
+
+def test_floquet_monodromy_and_exponents_cgl(bk):
+    """matrix-free Floquet monodromy of a Trapeze orbit of cGL (Floquet.jl:285-316) -- M-1 shifted JVPs and
+    shifted GMRES solves through the C ABI (a0 = 1, a1 = -+h/2) -- against the dense oracle; host-array orbit and
+    device-resident orbit (slices passed as raw device pointers of another context)."""
+    from oracle import floquet as ofl
+    nx, ny, M = 16, 12, 10
+    L = (np.pi, np.pi / 2)
+    pars = (1.3, 0.1, 1.0, -1.0, 1.0)
+    gl = problems.GinzburgLandau2D(nx, ny, *L, r=pars[0], mu=pars[1], nu=pars[2], c3=pars[3], c5=pars[4])
+    N = gl.N
+    ph = gl.phi11()
+    T = 6.4
+    x = np.concatenate([np.concatenate([0.5 * ph * np.cos(2 * np.pi * k / M), 0.5 * ph * np.sin(2 * np.pi * k / M)]) for k in range(M)] + [np.array([T])])
+    jac = lambda u: np.column_stack([gl.dF(u, e) for e in np.eye(N)])
+    mono = ofl.monodromy_dense(jac, x, M, N)
+    ctx_vf = bk.Context(bk.BK_CGL2D, (nx, ny), L, krylov_m=60, params=pars)
+    bk.floquet.cgl_shifted_precond(ctx_vf, T, M, pars[0])
+    ls = bk.GMRESB200(reltol=1e-12, restart=60, maxiter=60, Pr=True, orth="cgs2")
+    fl = bk.floquet.FloquetQaDB200(ctx_vf, ls, M, eigsolver=bk.floquet.ArnoldiLMB200(krylovdim=40, tol=1e-9))
+    v = np.random.default_rng(5).standard_normal(N)
+    assert _rel(fl.monodromy(x, v), mono @ v) < 1e-8                      # host buffers
+    ctx_po = bk.Context(bk.BK_POTRAP_CGL2D, (nx, ny, M), L, krylov_m=4, params=pars)
+    xd = ctx_po.to_device(x)
+    assert _rel(fl.monodromy(xd, ctx_vf.to_device(v)).numpy(), mono @ v) < 1e-8   # device-resident orbit
+    assert fl.all_converged and fl.solves == 2 * (M - 1)
+    sig, vecs, cv, info = fl(xd, 4)
+    ref, _ = ofl.floquet_exponents(np.linalg.eigvals(mono))
+    ref4 = ref[np.argsort(-np.abs(np.exp(ref)))][:4]
+    assert cv
+    assert np.allclose(np.sort(sig.real)[::-1], np.sort(ref4.real)[::-1], rtol=1e-6, atol=1e-8)
+    mu = info["multipliers"]
+    for k in range(4):
+        z = vecs[k][0].numpy() + 1j * vecs[k][1].numpy()
+        assert np.linalg.norm(mono @ z - mu[k] * z) < 1e-6 * abs(mu[k]) * np.linalg.norm(z)

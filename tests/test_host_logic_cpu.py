@@ -152,3 +152,54 @@ def test_all_gather_rows_gloo_world2():
     merged = np.array(res[0][2])
     assert merged.shape == (4 + 3 - 1, 4)                           # rank-1 segment starts at rank-0's last point (-0.13): dropped once
     assert np.all(np.diff(merged[:, 0]) < 0)
+
+
+# ------------------------------------------------------------------------------------------------ Floquet
+class NumpyVF:
+    """Duck-typed vector-field context (what floquet.py needs of a BK_CGL2D Context) on the NumPy cGL operator."""
+
+    def __init__(self, gl):
+        self.gl, self.u = gl, None
+
+    def jacobian(self, u):
+        self.u = np.array(u)
+        return self
+
+    def jvp(self, v, a0=0.0, a1=1.0):
+        return a0 * np.asarray(v) + a1 * self.gl.dF(self.u, np.asarray(v))
+
+
+def _dense_shifted_solver(gl):
+    def ls(J, rhs, a0=0.0, a1=1.0):
+        A = a0 * np.eye(gl.N) + a1 * np.column_stack([gl.dF(J.u, e) for e in np.eye(gl.N)])
+        return np.linalg.solve(A, rhs), True, 1
+    return ls
+
+
+def test_floquet_host_logic_matches_oracle():
+    """FloquetQaDB200 / ArnoldiLMB200 driven with NumPy vectors against oracle.floquet (Floquet.jl:285-316, 59-85)."""
+    from oracle import floquet as ofl
+    bk = g.load_package()
+    nx, ny, M = 6, 5, 9
+    gl = problems.GinzburgLandau2D(nx, ny, np.pi, np.pi / 2, r=1.3)
+    N = gl.N
+    ph = gl.phi11()
+    x = np.concatenate([np.concatenate([0.5 * ph * np.cos(2 * np.pi * k / M), 0.5 * ph * np.sin(2 * np.pi * k / M)]) for k in range(M)] + [np.array([6.4])])
+    jac = lambda u: np.column_stack([gl.dF(u, e) for e in np.eye(N)])
+    mono = ofl.monodromy_dense(jac, x, M, N)
+    fl = bk.floquet.FloquetQaDB200(NumpyVF(gl), _dense_shifted_solver(gl), M, eigsolver=bk.floquet.ArnoldiLMB200(krylovdim=40, tol=1e-10))
+    v = np.random.default_rng(5).standard_normal(N)
+    assert np.allclose(fl.monodromy(x, v), mono @ v, rtol=1e-10, atol=1e-12)
+    assert fl.solves == M - 1
+    sig, vecs, cv, info = fl(x, 4)
+    ref, _ = ofl.floquet_exponents(np.linalg.eigvals(mono))
+    ref4 = ref[np.argsort(-np.abs(np.exp(ref)))][:4]      # the 4 multipliers of largest modulus ...
+    ref4 = ref4[np.argsort(-ref4.real, kind="stable")]      # ... as exponents by decreasing real part
+    assert cv and np.allclose(np.sort(sig.real)[::-1], np.sort(ref4.real)[::-1], rtol=1e-7, atol=1e-9)
+    assert np.all(np.diff(sig.real) <= 1e-12)
+    mu = info["multipliers"]
+    for k in range(4):                                       # Ritz pairs really are eigenpairs of the monodromy
+        z = vecs[k][0] + 1j * vecs[k][1]
+        assert np.linalg.norm(mono @ z - mu[k] * z) < 1e-7 * abs(mu[k]) * np.linalg.norm(z)
+    sl = fl.extract_eigenvector(x, vecs[0][0])
+    assert len(sl) == M and np.allclose(sl[M - 2], mono @ vecs[0][0], rtol=1e-9, atol=1e-12)

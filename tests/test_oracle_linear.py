@@ -145,3 +145,17 @@ def test_shift_invert_vs_eigvals():
 def test_is_stable():
     ok, nu, ni = krylov.is_stable(np.array([0.1 + 0.2j, 0.1 - 0.2j, -1.0, 0.05]))
     assert (not ok) and nu == 3 and ni == 2
+
+
+def test_dst_helmholtz_precond_inverts_shifted_dirichlet_laplacian():
+    """oracle.precond.dst_helmholtz_precond == sparse solve with a0 I + a1 Lap (Dirichlet Laplacian of examples/cGL2d.jl:6-22)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from oracle import precond, problems
+    nx, ny = 24, 17
+    lap = problems.laplacian2d(nx, ny, np.pi, np.pi / 2, "dirichlet")
+    v = np.random.default_rng(0).standard_normal(nx * ny)
+    for a0, a1 in ((1.0, -0.3), (0.584, -0.32)):
+        ref = spl.spsolve((a0 * sp.identity(nx * ny) + a1 * lap).tocsc(), v)
+        got = precond.dst_helmholtz_precond(nx, ny, np.pi, np.pi / 2, a0, a1)(v)
+        assert np.linalg.norm(got - ref) < 1e-13 * np.linalg.norm(ref)

@@ -76,6 +76,23 @@ if "4" in which:
     ctx.sync(); t0 = time.perf_counter()
     dX, dl, ok, it = bls(Jpo, dR, tau, 0.7, rhs, 0.1, 0.5, 0.5, dotscale=1.0 / N)
     ctx.sync(); t_solve = time.perf_counter() - t0
+    # Floquet exponents of the orbit: matrix-free monodromy = M-1 shifted JVPs + shifted GMRES solves
+    floq = None
+    if os.environ.get("BK_PO_FLOQUET", "1") == "1":
+        try:
+            ctx_vf = bk.Context(bk.BK_CGL2D, (nx, ny), L, krylov_m=40, params=pars)
+            Tpo = float(upo[-1])
+            bk.floquet.cgl_shifted_precond(ctx_vf, Tpo, M, r)
+            lsf = bk.GMRESB200(reltol=1e-8, restart=40, maxiter=40, Pr=True)
+            fl = bk.floquet.FloquetQaDB200(ctx_vf, lsf, M, eigsolver=bk.floquet.ArnoldiLMB200(krylovdim=int(os.environ.get("BK_FLOQUET_KDIM", "16")), tol=1e-6, maxrestart=2))
+            ctx.sync(); ctx_vf.sync(); t0 = time.perf_counter()
+            sig, _, cvf, info = fl(po.u, 3)
+            ctx_vf.sync(); t_fl = time.perf_counter() - t0
+            floq = {"exponents_sigma": [[float(z.real), float(z.imag)] for z in sig], "converged": bool(cvf), "seconds": t_fl,
+                    "monodromy_applications": info["monodromy_applications"], "shifted_solves": info["solves"], "gmres_its": info["linear_its"]}
+            del ctx_vf
+        except Exception as e:  # keep the rest of the config line
+            floq = {"error": str(e)[:200]}
     # continuation of the periodic orbit in r: PALC + MatrixFreeBLS (continuation_po with linear_algo = MatrixFreeBLS(ls))
     prob2 = P.BifurcationProblemB200(ctx, po.u, pars, lens=0, record=lambda v: v.norminf())
     cp = P.ContinuationPar(dsmin=1e-4, dsmax=0.03, ds=0.001, p_min=r - 1.0, p_max=2.5, max_steps=8,   # cGL2d.jl:197 opts_po_cont
@@ -92,7 +109,7 @@ if "4" in which:
                       "po_residual_ms": t_res, "po_jvp_ms": t_jvp, "po_jvp_GBps": 24 * N / 1e6 / t_jvp, "precond_ms": t_pc,
                       "po_newton": {"converged": po.converged, "its": po.itnewton, "linear_its": po.itlineartot, "seconds": t_newton,
                                     "period_T": float(upo[-1]), "max_abs_u": float(np.max(np.abs(upo[:-1])))},
-                      "bordered_mf_solve_s": t_solve, "gmres_iters": it, "converged": ok,
+                      "bordered_mf_solve_s": t_solve, "gmres_iters": it, "converged": ok, "floquet": floq,
                       "po_continuation": {"steps": len(rows) - 1, "seconds": t_cont, "rows": [[round(q["param"], 6), round(q["x"], 6), q["itnewton"], q["itlinear"]] for q in rows]}}), flush=True)
     del ctx, x, dx, out, rhs, tau, dR
 
