@@ -14,3 +14,4 @@ from .core import (Context, DeviceVec, Jacobian, GMRESB200, BorderingBLSB200, Ma
 from . import palc
 from . import segments
 from . import floquet
+from . import events

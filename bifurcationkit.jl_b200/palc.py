@@ -114,6 +114,12 @@ class ContinuationPar:
     nev: int = 3
     detect_bifurcation: int = 0
     tol_stability: float = 1e-10
+    # events.py: fold detection by parameter monotony and bisection on the number of unstable eigenvalues
+    detect_fold: bool = True
+    n_inversion: int = 2
+    max_bisection_steps: int = 25
+    dsmin_bisection: float = 1e-16
+    tol_bisection_eigenvalue: float = 1e-16
 
 
 @dataclass
@@ -253,6 +259,9 @@ class ContState:
     nfail: int = 0
     work_newton: int = 0
     work_linear: int = 0
+    n_imag: tuple = (-1, -1)       # events.py: unstable eigenvalues with nonzero imaginary part (current, previous)
+    stepsizecontrol: bool = True   # events.py: switched off inside the bisection
+    in_bisection: bool = False
 
 
 def _secant(st, theta):

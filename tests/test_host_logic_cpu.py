@@ -203,3 +203,105 @@ def test_floquet_host_logic_matches_oracle():
         assert np.linalg.norm(mono @ z - mu[k] * z) < 1e-7 * abs(mu[k]) * np.linalg.norm(z)
     sl = fl.extract_eigenvector(x, vecs[0][0])
     assert len(sl) == M and np.allclose(sl[M - 2], mono @ vecs[0][0], rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ events
+def _default_eig(J, nev):
+    """DefaultEig (src/EigSolver.jl:31-50): dense spectrum, decreasing real part, first nev."""
+    vals = np.linalg.eigvals(np.asarray(J))
+    vals = vals[np.argsort(-vals.real, kind="stable")]
+    return vals[:nev], None, True, 1
+
+
+def _check_branch(br, cp, E):
+    """`testBranch` of test/continuation/test_bif_detection.jl:19-55 (the parts that do not need br.sol)."""
+    for i, row in enumerate(br.rows):
+        assert row["step"] == i == br.eig[i]["step"]
+        stable, nu, ni = E.is_stable(cp, br.eig[i]["eigenvals"])
+        assert row["n_unstable"] == nu and row["stable"] == stable
+    for bp in br.specialpoint:
+        if bp.type == "endpoint":
+            continue
+        i = bp.idx
+        nb = [br.rows[k]["n_unstable"] for k in (i - 1, i, i + 1) if 0 <= k < len(br.rows)]
+        assert len(set(nb)) > 1                      # states marked as bifurcation points sit next to a change of n_unstable
+        assert bp.interval[0] <= bp.param <= bp.interval[1]
+        assert bp.param == br.rows[i]["param"]
+
+
+def test_bifurcation_detection_and_bisection_known_answers():
+    """test/continuation/test_bif_detection.jl:57-100: F = -x + lambda L x - x^3 on the trivial branch; bifurcation points at
+    lambda = 1 / L_ii = 1,2,3,4,5 (multiplicity 1..5), 6, 6.5, 6.75, 6.875; located by bisection to 3e-3, from above."""
+    bk = g.load_package()
+    P, E = bk.palc, bk.events
+    Ld = np.array([1.0 / ii for ii in range(1, 6) for _ in range(ii)] + [1 / 6.0, 1 / 6.5, 1 / 6.75, 1 / 6.875])
+    F = lambda x, lam: -x + lam * Ld * x - x**3
+    J = lambda x, lam: np.diag(lam * Ld - 3 * x**2 - 1.0)
+    true_pts = np.array([1, 2, 3, 4, 5, 6, 6.5, 6.75, 6.875])
+    dims = [1, 2, 3, 4, 5, 1, 1, 1, 1]
+    nopts = P.NewtonPar(linsolver=krylov.DefaultLS(), eigsolver=_default_eig)
+    mk = lambda **kw: P.ContinuationPar(**{**dict(p_min=-1.0, p_max=10.0, ds=0.1, max_steps=150, detect_bifurcation=3, newton_options=nopts), **kw})
+    prob = lambda p0=0.0: NumpyProblem(F, J, np.zeros(len(Ld)), p0)
+    alg = P.PALC(bls=BlsAdapter(obls.MatrixBLS()))
+    # br1: default n_inversion = 2
+    cp1 = mk()
+    br1 = E.continuation(prob(), alg, cp1)
+    _check_branch(br1, cp1, E)
+    assert [abs(bp.delta[0]) for bp in br1.specialpoint if bp.type != "endpoint"] == dims
+    assert br1.specialpoint[-1].type == "endpoint"
+    # br2: n_inversion = 4, tol_bisection_eigenvalue = 1e-7 (:77-87)
+    cp2 = mk(p_max=10.3, n_inversion=4, tol_bisection_eigenvalue=1e-7)
+    br2 = E.continuation(prob(), alg, cp2)
+    _check_branch(br2, cp2, E)
+    pts = np.array([bp.param for bp in br2.specialpoint if bp.type != "endpoint"])
+    assert len(pts) == len(true_pts)
+    assert list(pts) > list(true_pts)                 # the reference's `specialpoint2 > specialpoints`
+    assert np.max(np.abs(pts - true_pts)) < 3e-3
+    assert [abs(bp.delta[0]) for bp in br2.specialpoint if bp.type != "endpoint"] == dims
+    assert all(bp.type == ("bp" if d == 1 else "nd") for bp, d in zip(br2.specialpoint, dims))
+    # br3: bisection "fails" (n_inversion = 8 cannot be reached within max_bisection_steps): intervals still valid (:90-92)
+    cp3 = mk(p_max=10.3, n_inversion=8, tol_bisection_eigenvalue=1e-7)
+    _check_branch(E.continuation(prob(), alg, cp3), cp3, E)
+    # br4: coming from above with a huge step and a single bisection step (:94-97)
+    cp4 = mk(p_max=1.95, n_inversion=8, ds=0.7, dsmax=1.5, max_bisection_steps=1)
+    _check_branch(E.continuation(prob(0.95), alg, cp4), cp4, E)
+
+
+def test_fold_and_hopf_detection_two_dimensional_field():
+    """test/continuation/test_bif_detection.jl:113-143: 2-d field with folds and Hopf points; detect_bifurcation = 3,
+    n_inversion = 6.  The branch invariants of `testBranch` hold and a Hopf point is found with a complex pair crossing."""
+    bk = g.load_package()
+    P, E = bk.palc, bk.events
+    k = 3
+
+    def F(X, p1):
+        x, y = X
+        return np.array([p1 + x - y - x**k / k, p1 + y + x - 2 * y**k / k])
+
+    def J(X, p1):
+        x, y = X
+        return np.array([[1 - x ** (k - 1), -1.0], [1.0, 1 - 2 * y ** (k - 1)]])
+
+    nopts = P.NewtonPar(max_iterations=5, linsolver=krylov.DefaultLS(), eigsolver=_default_eig)
+    cp = P.ContinuationPar(dsmax=0.1, ds=0.001, max_steps=135, p_min=-3.0, p_max=4.0, newton_options=nopts, detect_bifurcation=3,
+                           n_inversion=6, dsmin_bisection=1e-9, max_bisection_steps=15, nev=2)
+    br = E.continuation(NumpyProblem(F, J, -2 * np.ones(2), -3.0, record=lambda x: x[0]), P.PALC(bls=BlsAdapter(obls.MatrixBLS())), cp)
+    _check_branch(br, cp, E)
+    types = [bp.type for bp in br.specialpoint]
+    assert types[-1] == "endpoint" and "hopf" in types
+    hopf = [bp for bp in br.specialpoint if bp.type == "hopf"]
+    assert len(hopf) == 2 and abs(hopf[0].param + hopf[1].param) < 1e-4 and abs(abs(hopf[0].param) - 0.95385) < 1e-4
+    for bp in hopf:
+        assert abs(bp.delta[0]) == 2 and abs(bp.delta[1]) == 2 and bp.status == "converged"
+        assert bp.interval[1] - bp.interval[0] < 1e-4
+    # the field is odd-symmetric: the real eigenvalue crossings (folds of this branch) come in +- pairs
+    bps = sorted(bp.param for bp in br.specialpoint if bp.type == "bp")
+    assert len(bps) == 4 and abs(bps[0] + bps[3]) < 1e-5 and abs(bps[1] + bps[2]) < 2e-3
+    # without eigenvalues, folds are found from the parameter's monotony (detect_bifurcation < 2)
+    cp0 = P.ContinuationPar(dsmax=0.1, ds=0.001, max_steps=135, p_min=-3.0, p_max=4.0, newton_options=nopts, detect_bifurcation=0)
+    br0 = E.continuation(NumpyProblem(F, J, -2 * np.ones(2), -3.0, record=lambda x: x[0]), P.PALC(bls=BlsAdapter(obls.MatrixBLS())), cp0)
+    folds = [bp for bp in br0.specialpoint if bp.type == "fold"]
+    assert len(folds) == 4
+    for bp in folds:
+        i = bp.idx
+        assert (br0.rows[i + 1]["param"] - br0.rows[i]["param"]) * (br0.rows[i]["param"] - br0.rows[i - 1]["param"]) < 0
