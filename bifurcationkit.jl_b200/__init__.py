@@ -15,3 +15,4 @@ from . import palc
 from . import segments
 from . import floquet
 from . import events
+from . import deflation

@@ -305,3 +305,65 @@ def test_fold_and_hopf_detection_two_dimensional_field():
     for bp in folds:
         i = bp.idx
         assert (br0.rows[i + 1]["param"] - br0.rows[i]["param"]) * (br0.rows[i]["param"] - br0.rows[i - 1]["param"]) < 0
+
+
+# ------------------------------------------------------------------------------------------------ deflation
+def test_deflation_operator_problem_and_custom_linear_solver():
+    """test/newton/test_newton.jl:54-168: value of the deflation factor, Jacobian of M(u) F(u) against finite differences,
+    the Sherman-Morrison custom solver against a dense solve, deflated Newton finds the other root, two-guess Newton."""
+    bk = g.load_package()
+    P, D = bk.palc, bk.deflation
+    rng = np.random.default_rng(7)
+    # value of the factor (:70-87)
+    for acc in ("prod", "mean"):
+        op = D.DeflationOperator(2, 1.0, [rng.random(2) for _ in range(3)], accumulator=acc)
+        x0 = rng.random(2)
+        vals = [op.alpha + np.linalg.norm(x0 - r) ** (-2 * op.power) for r in op.roots]
+        ref = np.prod(vals) if acc == "prod" else np.mean(vals)
+        assert np.isclose(op(x0), ref, rtol=1e-8)
+    # Jacobian-vector product and custom linear solver (:125-143), F4def = (x - 1)(x - 2)
+    F = lambda x, p: (x - 1.0) * (x - 2.0)
+    J = lambda x, p: np.diag(2 * x - 3.0)
+    n = 3
+    op = D.DeflationOperator(2, 1.0, [1 + 0.01 * rng.random(n) for _ in range(3)])
+    prob = NumpyProblem(F, J, np.array([0.1] * n), None)
+    jprob = NumpyProblem(F, lambda x, p: (lambda dx, A=J(x, p): A @ dx), np.array([0.1] * n), None)  # J as an operator
+    dp, dpj = D.DeflatedProblem(prob, op), D.DeflatedProblem(jprob, op)
+    sol, rhs = rng.random(n), rng.random(n)
+    fd = lambda f, x: np.column_stack([(f(x + 1e-6 * e) - f(x - 1e-6 * e)) / 2e-6 for e in np.eye(len(x))])
+    Jfd = fd(lambda z: dp.F(z, None), sol)
+    assert np.allclose(dpj.jvp(sol, None, rhs), Jfd @ rhs, rtol=1e-5)
+    h, ok, its = D.DeflatedProblemCustomLS(krylov.DefaultLS())(dp.J(sol, None), rhs)
+    assert ok and np.allclose(h, np.linalg.solve(Jfd, rhs), rtol=1e-5)
+    # deflated Newton avoids the known root (:146-149)
+    for acc in ("prod", "mean"):
+        op1 = D.DeflationOperator(2, 1.0, [np.array([1.0])], accumulator=acc)
+        p1 = NumpyProblem(F, J, np.array([0.1]), None)
+        s = D.newton_deflated(p1, p1.u0, None, op1, P.NewtonPar(linsolver=krylov.DefaultLS()))
+        assert s.converged and np.isclose(s.u[0], 2.0, atol=1e-8)
+    # newton(prob, x0, x1, ...) (:160-168)
+    s1, s0, flag = D.newton_two_guesses(NumpyProblem(F, J, np.array([0.1]), None), np.array([1.2]), np.array([2.1]), None,
+                                        P.NewtonPar(linsolver=krylov.DefaultLS()))
+    assert flag and np.isclose(s0.u[0], 1.0) and np.isclose(s1.u[0], 2.0)
+
+
+def test_deflated_newton_finds_the_three_chan_solutions():
+    """The Chan/Bratu problem of examples/chan.jl at alpha = 3.3 sits on the S-shaped part of its branch: three solutions.
+    Plain Newton from sol0 finds the lower one; deflating it (and then the next) gives the other two."""
+    bk = g.load_package()
+    P, D = bk.palc, bk.deflation
+    n = 101
+    F = lambda x, a: problems.chan_F(x, a, 0.01)
+    J = lambda x, a: np.column_stack([problems.chan_dF(x, e, a, 0.01) for e in np.eye(n)])
+    prob = NumpyProblem(F, J, problems.chan_sol0(n), 3.3)
+    opts = P.NewtonPar(tol=1e-9, max_iterations=100, linsolver=krylov.DefaultLS())
+    s0 = P.newton(prob, prob.u0, 3.3, opts, P.norminf)
+    op = D.DeflationOperator(2, 1.0, [s0.u])
+    s1 = D.newton_deflated(prob, 4.0 * s0.u, 3.3, op, opts, P.norminf)
+    op.push(s1.u)
+    s2 = D.newton_deflated(prob, 8.0 * s0.u, 3.3, op, opts, P.norminf)
+    assert s0.converged and s1.converged and s2.converged
+    tops = sorted(float(np.max(s.u)) for s in (s0, s1, s2))
+    assert np.allclose(tops, [0.77197, 5.97988, 12.85103], atol=1e-4)
+    for s in (s0, s1, s2):
+        assert P.norminf(F(s.u, 3.3)) < 1e-8                  # roots of F itself, not only of M F
