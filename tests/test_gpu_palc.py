@@ -306,3 +306,52 @@ def test_floquet_monodromy_and_exponents_cgl(bk):
     for k in range(4):
         z = vecs[k][0].numpy() + 1j * vecs[k][1].numpy()
         assert np.linalg.norm(mono @ z - mu[k] * z) < 1e-6 * abs(mu[k]) * np.linalg.norm(z)
+
+
+def test_deflated_newton_three_chan_solutions_on_device(bk):
+    """SURVEY 8f.4 with device vectors: the Chan problem at alpha = 3.3 has three solutions (max u = 0.77197, 5.97988,
+    12.85103; CPU twin: tests/test_host_logic_cpu.py::test_deflated_newton_finds_the_three_chan_solutions).  Linear solves:
+    GMRESB200 with Pl = lu(P) (examples/chan.jl:108-111), two-rhs call inside DeflatedProblemCustomLS."""
+    P, D = bk.palc, bk.deflation
+    n = 101
+    ctx = bk.Context(bk.BK_CHAN, (n,), (1.0,), krylov_m=n, params=(3.3, 0.01))
+    ctx.precond_setup(bk.BK_PC_CHAN_TRIDIAG)
+    ls = bk.GMRESB200(reltol=1e-10, restart=n, maxiter=n, Pl=True, orth="cgs2")
+    prob = P.BifurcationProblemB200(ctx, ctx.to_device(problems.chan_sol0(n)), (3.3, 0.01), lens=0)
+    opts = P.NewtonPar(tol=1e-9, max_iterations=100, linsolver=ls)
+    s0 = P.newton(prob, prob.u0, 3.3, opts, P.norminf)
+    op = D.DeflationOperator(2, 1.0, [s0.u])
+    g1 = s0.u.copy(); g1.scale_(4.0)
+    s1 = D.newton_deflated(prob, g1, 3.3, op, opts, P.norminf)
+    op.push(s1.u)
+    g2 = s0.u.copy(); g2.scale_(8.0)
+    s2 = D.newton_deflated(prob, g2, 3.3, op, opts, P.norminf)
+    assert s0.converged and s1.converged and s2.converged
+    tops = sorted(float(np.max(s.u.numpy())) for s in (s0, s1, s2))
+    assert np.allclose(tops, [0.77197, 5.97988, 12.85103], atol=1e-4)
+
+
+def test_hopf_point_located_by_bisection_on_device(bk):
+    """SURVEY 8f.2 with device vectors: cGL2d 41 x 21 (the grid of examples/cGL2d.jl), trivial branch continued in r with
+    detect_bifurcation = 3; eigenvalues by ShiftInvertB200.  The first Hopf point is analytic, r_hopf = -lambda_1(Lap) = 1.14774
+    (examples/cGL2d.jl:120-135 reports it at r ~ 1.14), crossing pair +- i nu: delta = (2, 2)."""
+    P, E = bk.palc, bk.events
+    dims = (41, 21)
+    L = (np.pi, np.pi / 2)
+    r_hopf = problems.GinzburgLandau2D(*dims, *L).r_hopf()
+    pars = (r_hopf - 0.3, 0.1, 1.0, -1.0, 1.0)
+    ctx = bk.Context(bk.BK_CGL2D, dims, L, krylov_m=120, params=pars)
+    inner = bk.GMRESB200(reltol=1e-10, restart=120, maxiter=600, orth="cgs2")
+    eig = bk.ShiftInvertB200(0.5, inner, krylovdim=40, tol=1e-8, maxrestart=30)
+    ls = bk.GMRESB200(reltol=1e-10, restart=120, maxiter=240)
+    nopts = P.NewtonPar(tol=1e-9, max_iterations=10, linsolver=ls, eigsolver=eig)
+    cp = P.ContinuationPar(dsmin=1e-4, dsmax=0.05, ds=0.01, p_min=r_hopf - 0.5, p_max=r_hopf + 0.3, max_steps=60, newton_options=nopts,
+                           detect_bifurcation=3, n_inversion=6, nev=4, tol_stability=1e-8)
+    prob = P.BifurcationProblemB200(ctx, ctx.zeros(), pars, lens=0, record=lambda v: v.norminf())
+    br = E.continuation(prob, P.PALC(bls=bk.MatrixFreeBLSB200(ls)), cp, normC=P.norminf)
+    hopf = [bp for bp in br.specialpoint if bp.type == "hopf"]
+    assert len(hopf) == 1 and br.specialpoint[-1].type == "endpoint"
+    bp = hopf[0]
+    assert abs(bp.param - r_hopf) < 1e-5 and bp.delta == (2, 2) and bp.status == "converged"
+    assert bp.interval[0] <= bp.param <= bp.interval[1] and bp.interval[1] - bp.interval[0] < 1e-4
+    assert [row["n_unstable"] for row in br.rows][-1] == 2 and br.rows[0]["n_unstable"] == 0
