@@ -22,6 +22,57 @@
 #include "bk_common.cuh"
 
 #include "bk_dct.cuh"
+#include "bk_dct2.cuh"
+
+// Opt-in second version of the DCT kernels (bk_dct2.cuh; BK_DCT_V2=1).  Returns false when (n, W) has no instantiation.
+template <int LOGM, int LOGW>
+static bool launch_dct_v2(bk_ctx* c, int d, int mode, const double* in, double* out, const LineGeom& g, int nthr, const DctTables& tb,
+                          const SymbolArgs& sy) {
+  constexpr int W = 1 << LOGW;
+  const size_t sm = 16 * ((size_t)Dct2Cfg<LOGM>::MP * W + Dct2Cfg<LOGM>::TWN) + (mode == 2 ? 8 * (size_t)Dct2Cfg<LOGM>::N * W : 0);
+  static bool attr = false;
+  if (!attr) {
+    const int mx = 160 * 1024;
+    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    attr = true;
+  }
+  if (d == 0) {
+    dim3 grid((g.nouter + W - 1) / W);
+    if (mode == 0)
+      bk_launch_pdl(k_dct2v2<LOGM, LOGW, false, 0>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
+    else if (mode == 1)
+      bk_launch_pdl(k_dct2v2<LOGM, LOGW, false, 1>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
+    else
+      return false;
+  } else {
+    dim3 grid((g.nx + W - 1) / W, g.nouter);
+    if (mode == 0)
+      bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 0>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
+    else if (mode == 1)
+      bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 1>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
+    else
+      bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 2>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
+  }
+  return true;
+}
+static bool try_dct_v2(bk_ctx* c, int d, int mode, const double* in, double* out, const LineGeom& g, int W, int nthr, const DctTables& tb,
+                       const SymbolArgs& sy) {
+  static int on = -1;
+  if (on < 0) on = getenv("BK_DCT_V2") ? 1 : 0;
+  if (!on || nthr > 512) return false;
+  if (g.n == 2048 && W == 2) return launch_dct_v2<10, 1>(c, d, mode, in, out, g, nthr, tb, sy);
+  if (g.n == 1024 && W == 4) return launch_dct_v2<9, 2>(c, d, mode, in, out, g, nthr, tb, sy);
+  if (g.n == 1024 && W == 2) return launch_dct_v2<9, 1>(c, d, mode, in, out, g, nthr, tb, sy);
+  if (g.n == 512 && W == 8) return launch_dct_v2<8, 3>(c, d, mode, in, out, g, nthr, tb, sy);
+  if (g.n == 512 && W == 4) return launch_dct_v2<8, 2>(c, d, mode, in, out, g, nthr, tb, sy);
+  if (g.n == 256 && W == 16) return launch_dct_v2<7, 4>(c, d, mode, in, out, g, nthr, tb, sy);
+  if (g.n == 256 && W == 8) return launch_dct_v2<7, 3>(c, d, mode, in, out, g, nthr, tb, sy);
+  return false;
+}
 
 // dense transform of every line: out[line, k] = sum_e M[k*n + e] in[line, e]
 static __global__ void __launch_bounds__(256) k_dense_lines(const double* __restrict__ in, double* __restrict__ out, LineGeom g,
@@ -322,6 +373,11 @@ static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* o
     DctTables tb{pc.tw[d], pc.wn[d], pc.dtw[d]};
     SymbolArgs sy{nullptr, nullptr, nullptr, 0.0, nullptr, nullptr, 0};
     if (fused_sym) sy = *fused_sym;
+    if (try_dct_v2(c, d, mode, in, out, g, W, nthr, tb, sy)) {
+      c->stats.kernel_launches++;
+      BK_CUDA(c, cudaGetLastError());
+      return BK_OK;
+    }
     static bool attr = false;
     if (!attr) {
       const int mx = 160 * 1024;

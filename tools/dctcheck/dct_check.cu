@@ -8,7 +8,9 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <type_traits>
 #include "bk_dct.cuh"
+#include "bk_dct2.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
@@ -119,5 +121,37 @@ int main(int argc, char** argv) {
   timeit("y forward  k_dct2<1,0>", [&] { fy(x, a); }, 16.0 * N);
   timeit("y fused    k_dct2<1,2>", [&] { fused_y(a, b); }, 16.0 * N);
   timeit("preconditioner (3 launches)", [&] { fx(x, a); fused_y(a, b); ix(b, c2); }, 48.0 * N);
+  // ---- version 2 (bk_dct2.cuh), n = 1024 / W = 4 and n = 512 / W = 8 instantiated here
+  auto v2 = [&](auto LM, auto LW) {
+    constexpr int LOGM = decltype(LM)::value, LOGW = decltype(LW)::value;
+    if ((2 << LOGM) != n || (1 << LOGW) != W) return;
+    const size_t s1 = 16 * ((size_t)Dct2Cfg<LOGM>::MP * W + Dct2Cfg<LOGM>::TWN), s2 = s1 + 8 * (size_t)n * W;
+    CK(cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CK(cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CK(cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CK(cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CK(cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    auto fx2 = [&](const double* in, double* out) { return bk_launch_pdl(k_dct2v2<LOGM, LOGW, false, 0>, grid_x, dim3(nthr), s1, 0, in, out, gx, tb, none); };
+    auto ix2 = [&](const double* in, double* out) { return bk_launch_pdl(k_dct2v2<LOGM, LOGW, false, 1>, grid_x, dim3(nthr), s1, 0, in, out, gx, tb, none); };
+    auto fy2 = [&](const double* in, double* out) { return bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 0>, grid_y, dim3(nthr), s1, 0, in, out, gy, tb, none); };
+    auto iy2 = [&](const double* in, double* out) { return bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 1>, grid_y, dim3(nthr), s1, 0, in, out, gy, tb, none); };
+    auto fu2 = [&](const double* in, double* out) { return bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 2>, grid_y, dim3(nthr), s2, 0, in, out, gy, tb, sy); };
+    double *r1, *r2; CK(cudaMalloc(&r1, 8 * N)); CK(cudaMalloc(&r2, 8 * N));
+    CK(fx(x, r1)); CK(fx2(x, a)); printf("  v2 x forward vs v1   rel err %.2e\n", maxdiff(a, r1, N));
+    CK(ix(r1, r2)); CK(ix2(r1, a)); printf("  v2 x inverse vs v1   rel err %.2e\n", maxdiff(a, r2, N));
+    CK(fy(x, r1)); CK(fy2(x, a)); printf("  v2 y forward vs v1   rel err %.2e\n", maxdiff(a, r1, N));
+    CK(iy(r1, r2)); CK(iy2(r1, a)); printf("  v2 y inverse vs v1   rel err %.2e\n", maxdiff(a, r2, N));
+    CK(fused_y(x, r1)); CK(fu2(x, a)); printf("  v2 y fused vs v1     rel err %.2e\n", maxdiff(a, r1, N));
+    timeit("v2 x forward", [&] { fx2(x, a); }, 16.0 * N);
+    timeit("v2 x inverse", [&] { ix2(a, b); }, 16.0 * N);
+    timeit("v2 y forward", [&] { fy2(x, a); }, 16.0 * N);
+    timeit("v2 y fused", [&] { fu2(a, b); }, 16.0 * N);
+    timeit("v2 preconditioner (3 launches)", [&] { fx2(x, a); fu2(a, b); ix2(b, c2); }, 48.0 * N);
+  };
+  v2(std::integral_constant<int, 9>{}, std::integral_constant<int, 2>{});
+  v2(std::integral_constant<int, 9>{}, std::integral_constant<int, 1>{});
+  v2(std::integral_constant<int, 9>{}, std::integral_constant<int, 3>{});
+  v2(std::integral_constant<int, 8>{}, std::integral_constant<int, 3>{});
+  v2(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
   return 0;
 }
