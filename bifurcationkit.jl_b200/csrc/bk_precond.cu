@@ -277,6 +277,12 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
       double h = 2 * c->lengths[d] / c->dims[d];
       BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1));
     }
+    if (getenv("BK_CGL_DST_GEMM") && !pc.blas) {  // opt-in: dense DST-I through cuBLAS instead of k_dense_lines (see apply)
+      cublasHandle_t hnd;
+      BK_CHECK(c, cublasCreate(&hnd) == CUBLAS_STATUS_SUCCESS, "cublasCreate failed");
+      cublasSetStream(hnd, c->stream);
+      pc.blas = (void*)hnd;
+    }
   } else if (kind == BK_PC_POTRAP_CIRC) {
     BK_CHECK(c, c->kind == BK_POTRAP_CGL2D, "BK_PC_POTRAP_CIRC needs a Trapeze (potrap) context");
     const int K = (int)c->dims[2] - 1;
@@ -476,6 +482,28 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
     const long long nblk = (c->kind == BK_POTRAP_CGL2D) ? 2 * c->dims[2] : 2;  // components x slices
     double* A = pc.work;
     double* B = pc.work2;
+    if (pc.blas && getenv("BK_CGL_DST_GEMM")) {
+      // Opt-in (not yet run on a GPU): the four dense DST-I passes as GEMMs, as BK_PC_POTRAP_CIRC does.  k_dense_lines costs
+      // 2.4 ms per apply at 512^2 x 2 fields (Floquet: 21 s for 48 monodromy applications); the GEMMs should be ~0.15 ms.
+      cublasHandle_t hnd = (cublasHandle_t)pc.blas;
+      const double one = 1.0, zero = 0.0;
+      const long long nn = (long long)nx * ny;
+      const int nf = (int)nblk;
+      const double* Sx = pc.dense[0];
+      const double* Sy = pc.dense[1];
+      BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, in, nx, &zero, A, nx) ==
+                      CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
+      BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, A, nx, nn, Sy, ny, 0, &zero, B, nx, nn,
+                                            nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
+      k_helmholtz_symbol_div<<<lin_grid(c, nn * nblk), 256, 0, c->stream>>>(B, nx, ny, nblk, pc.lam[0], pc.lam[1], pc.a0, pc.a1);
+      BK_CUDA(c, cudaGetLastError());
+      BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, B, nx, nn, Sy, ny, 0, &zero, A, nx, nn,
+                                            nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
+      BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, A, nx, &zero, out, nx) ==
+                      CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
+      c->stats.kernel_launches += 5;
+      if (c->kind == BK_POTRAP_CGL2D) BK_CUDA(c, cudaMemcpyAsync(out + N - 1, in + N - 1, 8, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
     BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, (int)nblk));
     BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, (int)nblk));
     k_helmholtz_symbol_div<<<lin_grid(c, (long long)nx * ny * nblk), 256, 0, c->stream>>>(B, nx, ny, nblk, pc.lam[0], pc.lam[1],
@@ -485,6 +513,7 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
     BK_TRY(transform_pass(c, 1, -1, B, A, nx, ny, (int)nblk));
     BK_TRY(transform_pass(c, 0, -1, A, out, nx, ny, (int)nblk));
     if (c->kind == BK_POTRAP_CGL2D) BK_CUDA(c, cudaMemcpyAsync(out + N - 1, in + N - 1, 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
   } else if (pc.kind == BK_PC_POTRAP_CIRC) {
     const int nx = (int)c->dims[0], ny = (int)c->dims[1], M = (int)c->dims[2];
     const long long nn = (long long)nx * ny, Ns = 2 * nn;
