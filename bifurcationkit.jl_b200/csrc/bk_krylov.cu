@@ -485,10 +485,12 @@ static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lon
     BK_TRY(launch_update(c, vnext, n, j, vnext, hcol + j, c->scales + k + 1));
   }
   BK_CUDA(c, cudaEventRecord(c->events[k], c->stream));
-  c->stats.last_fused_bytes += 8LL * n * (2LL * j + 4);
+  // algorithmic bytes of the step: B(j) = 8N(2j+4); the bordered map reads a and b as well (+16N, "40N" K2')
+  const long long step_bytes = 8LL * n * (2LL * j + 4) + (op.bordered ? 16LL * n : 0LL);
+  c->stats.last_fused_bytes += step_bytes;
   c->stats.last_fused_launches += 2;
   if (fuse) {
-    c->stats.total_fused_bytes += 8LL * n * (2LL * j + 4);
+    c->stats.total_fused_bytes += step_bytes;
     c->stats.total_fused_launches += 2;
   }
   return BK_OK;
