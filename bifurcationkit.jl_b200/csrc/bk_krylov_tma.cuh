@@ -294,7 +294,9 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
                                                                   double* __restrict__ partials, unsigned int* counter,
                                                                   double* __restrict__ hcol, double* __restrict__ gcoef,
                                                                   int NS, int sred_off) {
+#ifndef BK2_LATE_WAIT
   bk_pdl_sync();
+#endif
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
   __shared__ int s_flag;
@@ -304,6 +306,11 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
   const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
   const int x0 = (blockIdx.x % tiles_x) * BK2_ROW, y0 = (blockIdx.x / tiles_x) * E;
   double val[E];
+#ifdef BK2_LATE_WAIT
+  // experiment (build with EXTRA=-DBK2_LATE_WAIT, not yet measured): barrier set-up and tile arithmetic overlap the tail of
+  // the previous kernel; nothing written by it has been read yet (the L2 prefetch below is only a hint)
+  bk_pdl_sync();
+#endif
   const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
   Tile2 tl;
   tl.base = x0 + (long long)y0 * op.nx;
