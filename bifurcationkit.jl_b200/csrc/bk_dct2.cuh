@@ -8,7 +8,12 @@
 //   * shared-memory indices are 32-bit; for passes with half >= 8 the four butterfly addresses are base + c * const;
 //   * the FFT twiddles are staged once per CTA in shared memory;
 //   * post- and pre-processing handle the pair (k, M-k) together: V[M-k] = conj(ev - wn[k] od) reuses everything;
-//   * the contiguous direction moves two values per thread and access (x[2j], x[2j+1] are neighbours in memory).
+//   * the contiguous direction moves two values per thread and access (x[2j], x[2j+1] are neighbours in memory);
+//   * shared-memory bank conflicts (v1: 1.59 wavefronts per ideal wavefront in ncu) are designed out with the model in
+//     tools/dctcheck/bank_model.py: index padding i + i/8 + i/64 (the bit-reversed scatter of the load phase strides by
+//     M/16, which i + i/8 alone maps onto one bank: 8-way), per-pass twiddle tables that are contiguous in the butterfly
+//     position (a strided read of one table is 8-way), and for the passes with half < 8 a lane order in which the group index
+//     runs fastest.  Model, n = 1024 / W = 4: 2.42 -> 1.06 (x kernels), 1.33 -> 1.24 (y kernels).
 // STATUS: opt-in (BK_DCT_V2=1, see bk_precond.cu).  Checked against a naive DCT on the host by compiling this header with
 // BK_DCT_HOST_EMU (tools/dctcheck/dct2_host_emu.cpp: one emulated thread per CTA runs every phase to completion, which is
 // exact because the items of a phase are independent); NOT yet run or timed on a GPU -- tools/dctcheck/dct_check.cu does both.
@@ -17,11 +22,16 @@
 #include "bk_dct.cuh"
 #endif
 
+// per-pass twiddle tables: pass ST (= P0, P0 + 2, ...) holds w1[pos], w2[pos], pos < 2^ST, at offset 2 (2^ST - 2^P0) / 3
+__host__ __device__ constexpr int d2_tw_off(int st, int p0) { return 2 * ((1 << st) - (1 << p0)) / 3; }
+
 template <int LOGM>
 struct Dct2Cfg {
-  static constexpr int M = 1 << LOGM, N = 2 * M, MP = M + (M >> 3) + 1, TWN = M / 2;
+  static constexpr int M = 1 << LOGM, N = 2 * M, P0 = LOGM & 1;
+  static constexpr int MP = (M - 1) + ((M - 1) >> 3) + ((M - 1) >> 6) + 1;  // d2_pad(M - 1) + 1
+  static constexpr int TWN = 2 * (M - (1 << P0)) / 3;
 };
-__device__ __forceinline__ int d2_pad(int i) { return i + (i >> 3); }
+__device__ __forceinline__ int d2_pad(int i) { return i + (i >> 3) + (i >> 6); }
 __device__ __forceinline__ double2 d2_cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 d2_conj(double2 a) { return make_double2(a.x, -a.y); }
 __device__ __forceinline__ double2 d2_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -37,20 +47,28 @@ __device__ __forceinline__ int d2_slot(int line, int pi) {
 template <int LOGM, int LOGW, bool STRIDED, int ST>
 __device__ __forceinline__ void d2_pass4(double2* s, const double2* stw, bool inverse) {
   constexpr int M = 1 << LOGM, W = 1 << LOGW, HALF = 1 << ST;
+  const double2* w1t = stw + d2_tw_off(ST, LOGM & 1);
+  const double2* w2t = w1t + HALF;
   for (int g = threadIdx.x; g < (M >> 2) * W; g += blockDim.x) {
     const int line = STRIDED ? (g & (W - 1)) : (g >> (LOGM - 2));
-    const int gi = STRIDED ? (g >> LOGW) : (g & ((M >> 2) - 1));
+    int gi = STRIDED ? (g >> LOGW) : (g & ((M >> 2) - 1));
+    if (!STRIDED && ST > 0 && ST < 3 && (M >> 2) >= 8 * HALF) {
+      // line-major layout, half < 8: within a block of 8 * HALF butterflies let the group index run fastest over the lanes
+      // (a quarter-warp then touches 8 different groups = 8 different bank groups instead of 8 / HALF)
+      const int r = gi & (8 * HALF - 1);
+      gi = (gi & ~(8 * HALF - 1)) + ((r & 7) << ST) + (r >> 3);
+    }
     const int pos = gi & (HALF - 1);
     const int i = ((gi >> ST) << (ST + 2)) + pos;
-    double2 w1 = stw[pos << (LOGM - ST - 1)], w2 = stw[pos << (LOGM - ST - 2)];
+    double2 w1 = w1t[pos], w2 = w2t[pos];
     if (inverse) {
       w1.y = -w1.y;
       w2.y = -w2.y;
     }
     const double2 w3 = inverse ? make_double2(-w2.y, w2.x) : make_double2(w2.y, -w2.x);  // w2 * (+-i)
     int ia, ib, ic, id;
-    if (HALF >= 8) {  // (c * HALF) is a multiple of 8: pad(i + c HALF) = pad(i) + c (HALF + HALF / 8)
-      constexpr int STEP = HALF + (HALF >> 3);
+    if (HALF >= 64) {  // (c * HALF) is a multiple of 64: pad(i + c HALF) = pad(i) + c (HALF + HALF / 8 + HALF / 64)
+      constexpr int STEP = HALF + (HALF >> 3) + (HALF >> 6);
       ia = d2_pad(i);
       ib = ia + STEP;
       ic = ia + 2 * STEP;
@@ -112,7 +130,7 @@ __device__ __forceinline__ void d2_fft(double2* s, const double2* stw, bool inve
 }
 
 // MODE 0: forward, 1: inverse, 2: forward + divide by the operator symbol + inverse.
-// shared memory: s[MP * W] complex | stw[M / 2] complex | (MODE 2) cb[N * W] real
+// shared memory: s[MP * W] complex | stw[TWN] complex (per-pass twiddle tables) | (MODE 2) cb[N * W] real
 template <int LOGM, int LOGW, bool STRIDED, int MODE>
 static __global__ void __launch_bounds__(512) k_dct2v2(const double* __restrict__ in, double* __restrict__ out, LineGeom g, DctTables tb,
                                                        SymbolArgs sy) {
@@ -143,7 +161,14 @@ static __global__ void __launch_bounds__(512) k_dct2v2(const double* __restrict_
   const long long es = g.es;
   const double inv_m = 1.0 / M;
   if (sy.tail_n > 0 && blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < sy.tail_n) sy.tail_dst[threadIdx.x] = sy.tail_src[threadIdx.x];
-  for (int q = threadIdx.x; q < C::TWN; q += blockDim.x) stw[q] = __ldg(tb.tw + q);
+  for (int st = C::P0; st < LOGM; st += 2) {  // per-pass twiddle tables: w1[pos] = tw[pos M / 2^(st+1)], w2[pos] = tw[pos M / 2^(st+2)]
+    const int half = 1 << st;
+    double2* t = stw + d2_tw_off(st, C::P0);
+    for (int q = threadIdx.x; q < 2 * half; q += blockDim.x) {
+      const int pos = q & (half - 1);
+      t[q] = __ldg(tb.tw + (q < half ? (pos << (LOGM - st - 1)) : (pos << (LOGM - st - 2))));
+    }
+  }
 
   // ---------------------------------------------------------------- forward half (MODE 0, 2)
   if (MODE != 1) {

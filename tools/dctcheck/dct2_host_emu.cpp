@@ -14,6 +14,7 @@ struct Idx3 { int x = 0, y = 0, z = 0; };
 static Idx3 threadIdx, blockIdx, blockDim, gridDim;
 #define __global__
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
