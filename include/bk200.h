@@ -154,6 +154,13 @@ int32_t bk_hessenberg_eig(const double* H, int32_t n, int32_t ldh, double* wr, d
  *   (BK_POTRAP_CGL2D contexts; x = [x_1..x_M; T], src/periodicorbit/PeriodicOrbitTrapeze.jl:249-330) */
 int32_t bk_potrap_set_section(bk_ctx* ctx, const double* phi, const double* xpi); /* length N-1 each */
 
+/* ---- environment switches read once by the library (tuning / diagnostics; none is needed for normal use)
+ *   BK2_E=1..8          tile height of the TMA-ring Arnoldi kernels instead of the heuristic (bk_krylov.cu::plan2)
+ *   BK_NO_PDL=1         launch without programmatic dependent launch (plain stream order)
+ *   BK_DCT_W, BK_DCT_THREADS   lines per CTA / threads per CTA of the DCT kernels
+ *   BK_DCT_V2=1         second version of the DCT kernels (bk_dct2.cuh) -- opt-in until it has been validated on a GPU
+ *   BK_CGL_DST_GEMM=1   BK_PC_CGL_DST through cuBLAS GEMMs instead of the dense-line kernel -- opt-in, same status */
+
 #ifdef __cplusplus
 }
 #endif
