@@ -34,7 +34,7 @@ extern "C" int32_t bk_bls_bordering(bk_ctx* c, const double* dR, const double* d
                                     double xiu, double xip, int32_t has_shift, double shift, double dotscale,
                                     const bk_gmres_opts* opts, int32_t check_precision, int32_t kmax, double tol, double* dX,
                                     double* dl, int32_t* converged, int32_t iters[2]) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   BK_CHECK(c, opts != nullptr, "opts required");
   const long long N = c->N;
@@ -88,7 +88,7 @@ static __global__ void k_set_tail(double* v, long long idx, double val) { v[idx]
 extern "C" int32_t bk_bls_matrixfree(bk_ctx* c, const double* dR, const double* dzu, double dzp, const double* R, double n,
                                      double xiu, double xip, int32_t has_shift, double shift, double dotscale,
                                      const bk_gmres_opts* opts, double* dX, double* dl, int32_t* converged, int32_t* iters) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   BK_CHECK(c, opts != nullptr, "opts required");
   const long long N = c->N;

@@ -105,10 +105,13 @@ struct bk_ctx {
   double* eig_dev = nullptr; // ones (qcap+2) | hcolA (qcap+2) | hcolB (qcap+2) | g (qcap+2) | coef (2*(qcap+2))
   double* eig_pinned = nullptr;
   Precond pc;
-  bk_stats stats = {0, 0, 0, 0.0, 0, 0, 0.0, 0, 0};
+  bk_stats stats = {};
   bool timing = false;
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tpairs;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize already granted per kernel ON THIS CONTEXT'S DEVICE (the attribute is per
+  // device: a process-wide cache would leave a second GPU's copy of the kernel at the 48 KB default)
+  std::unordered_map<const void*, size_t> smem_attr;
   std::string err;
 };
 
@@ -122,6 +125,14 @@ int bk_fail(bk_ctx* c, int code, const char* what, const char* file, int line);
 #define BK_CHECK(c, cond, msg)                                                       \
   do {                                                                               \
     if (!(cond)) return bk_fail((c), BK_ERR_ARG, (msg), __FILE__, __LINE__);         \
+  } while (0)
+// first statement of every extern "C" entry point: a process may hold contexts on several GPUs (Context(device=...)),
+// and kernel launches / cudaFuncSetAttribute / cudaMalloc all act on the CURRENT device
+#define BK_ENTER(c)                                 \
+  do {                                              \
+    if (!(c)) return BK_ERR_ARG;                    \
+    if (cudaSetDevice((c)->device) != cudaSuccess)  \
+      return bk_fail((c), BK_ERR_CUDA, "cudaSetDevice failed", __FILE__, __LINE__); \
   } while (0)
 #define BK_TRY(expr)                 \
   do {                               \
@@ -165,6 +176,17 @@ int bk_launch_lincomb(bk_ctx* c, const double* basis, const double* scales, doub
                       const double* coef_dev);
 int bk_tmp(bk_ctx* c, int slot, double** out);  // lazily allocated ld-sized temporaries
 
+// grant `bytes` of dynamic shared memory to `kern` on the context's device (cached per context)
+template <typename K>
+static inline void bk_ensure_smem(bk_ctx* c, K kern, size_t bytes) {
+  size_t& cur = c->smem_attr[(const void*)kern];
+  if (bytes > cur) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cur = bytes;
+  }
+}
+
 // ---- programmatic dependent launch (PDL): the next kernel of the stream is launched while this one drains ---------
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
@@ -199,9 +221,12 @@ __device__ __forceinline__ double bk_warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// NaN-propagating max: fmax() drops NaN, which would turn an all-NaN residual into norminf = 0 ("converged").
+// norm(x, Inf) of the reference returns NaN there and the step is rejected (src/continuation/Palc.jl:228-231).
+__device__ __forceinline__ double bk_nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
 __device__ __forceinline__ double bk_warp_max(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = bk_nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 // Grid-wide "last block done" ticket.  Returns true in exactly one block (the last to arrive),

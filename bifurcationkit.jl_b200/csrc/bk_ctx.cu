@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include "bk_common.cuh"
+#include "bk_stencil.cuh"
 
 int bk_fail(bk_ctx* c, int code, const char* what, const char* file, int line) {
   if (c) {
@@ -110,6 +111,16 @@ extern "C" int32_t bk_ctx_create(int32_t device, int32_t kind, const int64_t dim
   BK_CUDA(c, cudaMallocHost(&c->h_pinned, 2 * 8 * (m + 1) * (m + 4)));
   // number of partial-sum columns: one per CTA of the widest reduction grid
   long long g = (n + 2 + 255) / 256 + 8;  // worst case: one CTA per 256 values
+  if (kind == BK_SH2D) {
+    // the fused 2-D kernel tiles rows, not the flat vector: a narrow grid (nx << 256) has up to ceil(nx/256) * ny CTAs
+    long long gf = ((c->dims[0] + 255) / 256) * c->dims[1] + 8;
+    if (gf > g) g = gf;
+  }
+  if (kind == BK_SH2D || kind == BK_SH3D) {  // first-generation tile kernels (64x32 / 32x8x8 tiles, ragged grids)
+    long long gt = kind == BK_SH2D ? sh_num_tiles<2>((int)c->dims[0], (int)c->dims[1], 1)
+                                   : sh_num_tiles<3>((int)c->dims[0], (int)c->dims[1], (int)c->dims[2]);
+    if (gt + 8 > g) g = gt + 8;
+  }
   if (g < 4 * c->nsm) g = 4 * c->nsm;
   c->gmax = (int)g;
   BK_CUDA(c, cudaMalloc(&c->partials, 8 * (m + 4) * (size_t)c->gmax));
@@ -176,23 +187,24 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
 extern "C" const char* bk_last_error(bk_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" int64_t bk_problem_size(bk_ctx* c) { return c ? c->N : 0; }
 extern "C" int32_t bk_set_params(bk_ctx* c, const double* p, int32_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, p && n >= 0 && n <= BK_MAX_PAR, "bad params");
   for (int i = 0; i < n; ++i) c->par[i] = p[i];
   return BK_OK;
 }
 extern "C" int32_t bk_get_stats(bk_ctx* c, bk_stats* out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   *out = c->stats;
   return BK_OK;
 }
 extern "C" int32_t bk_set_timing(bk_ctx* c, int32_t on) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   c->timing = on != 0;
   return BK_OK;
 }
 extern "C" int32_t bk_sync(bk_ctx* c) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
   return BK_OK;
 }
@@ -200,7 +212,8 @@ extern "C" void* bk_stream(bk_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 // ---- vectors -----------------------------------------------------------------------------------
 extern "C" int32_t bk_vec_alloc(bk_ctx* c, int64_t n, double** out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   BK_CHECK(c, n > 0, "bad length");
   BK_CUDA(c, cudaSetDevice(c->device));
   size_t len = ((size_t)n + 31) / 32 * 32;
@@ -221,7 +234,7 @@ extern "C" int32_t bk_vec_alloc(bk_ctx* c, int64_t n, double** out) {
   return BK_OK;
 }
 extern "C" int32_t bk_vec_free(bk_ctx* c, double* v) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   if (v) {
     auto it = c->vec_live.find(v);
     BK_CHECK(c, it != c->vec_live.end(), "bk_vec_free: pointer was not allocated by bk_vec_alloc of this context");
@@ -232,14 +245,15 @@ extern "C" int32_t bk_vec_free(bk_ctx* c, double* v) {
 // pinned host buffers for option-A callers (host-resident state): H2D/D2H at PCIe speed instead of the
 // pageable-memory staging path
 extern "C" int32_t bk_host_alloc(bk_ctx* c, int64_t n, double** out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   BK_CHECK(c, n > 0, "bad length");
   BK_CUDA(c, cudaSetDevice(c->device));
   BK_CUDA(c, cudaHostAlloc((void**)out, 8 * (size_t)n, cudaHostAllocDefault));
   return BK_OK;
 }
 extern "C" int32_t bk_host_free(bk_ctx* c, double* p) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   if (p) {
     BK_CUDA(c, cudaStreamSynchronize(c->stream));
     BK_CUDA(c, cudaFreeHost(p));
@@ -247,14 +261,14 @@ extern "C" int32_t bk_host_free(bk_ctx* c, double* p) {
   return BK_OK;
 }
 extern "C" int32_t bk_vec_upload(bk_ctx* c, double* dst, const double* src, int64_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CUDA(c, cudaMemcpyAsync(dst, src, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stats.h2d_bytes += 8 * n;
   return BK_OK;
 }
 extern "C" int32_t bk_vec_download(bk_ctx* c, double* dst, const double* src, int64_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CUDA(c, cudaMemcpyAsync(dst, src, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stats.d2h_bytes += 8 * n;
@@ -315,7 +329,7 @@ static __global__ void __launch_bounds__(256) k_reduce(const double* __restrict_
   double acc = 0.0;
   for (; i < n; i += stride) {
     if (MODE == 0) acc = fma(x[i], y[i], acc);
-    if (MODE == 1) acc = fmax(acc, fabs(x[i]));
+    if (MODE == 1) acc = bk_nanmax(acc, fabs(x[i]));
     if (MODE == 2) acc = fma(x[i] - x0[i], y[i], acc);
   }
   acc = (MODE == 1) ? bk_warp_max(acc) : bk_warp_sum(acc);
@@ -324,21 +338,21 @@ static __global__ void __launch_bounds__(256) k_reduce(const double* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = s_w[0];
-    for (int k = 1; k < 8; ++k) t = (MODE == 1) ? fmax(t, s_w[k]) : t + s_w[k];
+    for (int k = 1; k < 8; ++k) t = (MODE == 1) ? bk_nanmax(t, s_w[k]) : t + s_w[k];
     partials[blockIdx.x] = t;
   }
   if (bk_last_block(counter, &s_flag)) {
     double t = 0.0;
     for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
       double v = __ldcg(partials + k);
-      t = (MODE == 1) ? fmax(t, v) : t + v;
+      t = (MODE == 1) ? bk_nanmax(t, v) : t + v;
     }
     t = (MODE == 1) ? bk_warp_max(t) : bk_warp_sum(t);
     if (lane == 0) s_w[wid] = t;
     __syncthreads();
     if (threadIdx.x == 0) {
       double r = s_w[0];
-      for (int k = 1; k < 8; ++k) r = (MODE == 1) ? fmax(r, s_w[k]) : r + s_w[k];
+      for (int k = 1; k < 8; ++k) r = (MODE == 1) ? bk_nanmax(r, s_w[k]) : r + s_w[k];
       out[0] = r;
     }
   }
@@ -366,36 +380,38 @@ int bk_dev_norminf(bk_ctx* c, const double* x, long long n, double* out_host) {
 #define BK_DEVPTR(c, p) BK_CHECK(c, (p) && bk_is_device_ptr(p), "bk_vec_* needs device pointers from bk_vec_alloc")
 
 extern "C" int32_t bk_vec_copy(bk_ctx* c, double* dst, const double* src, int64_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_DEVPTR(c, dst);
   BK_DEVPTR(c, src);
   return bk_dev_copy(c, dst, src, n);
 }
 extern "C" int32_t bk_vec_zero(bk_ctx* c, double* x, int64_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_DEVPTR(c, x);
   BK_CUDA(c, cudaMemsetAsync(x, 0, 8 * (size_t)n, c->stream));
   return BK_OK;
 }
 extern "C" int32_t bk_vec_scale(bk_ctx* c, double* x, double a, int64_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_DEVPTR(c, x);
   return bk_dev_scale(c, x, a, n);
 }
 extern "C" int32_t bk_vec_axpby(bk_ctx* c, double* y, double a, const double* x, double b, int64_t n) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_DEVPTR(c, y);
   BK_DEVPTR(c, x);
   return bk_dev_axpby(c, y, a, x, b, n);
 }
 extern "C" int32_t bk_vec_dot(bk_ctx* c, const double* x, const double* y, int64_t n, double* out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   BK_DEVPTR(c, x);
   BK_DEVPTR(c, y);
   return bk_dev_dot(c, x, y, n, out);
 }
 extern "C" int32_t bk_vec_norm2(bk_ctx* c, const double* x, int64_t n, double* out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   BK_DEVPTR(c, x);
   double d = 0;
   BK_TRY(bk_dev_dot(c, x, x, n, &d));
@@ -403,12 +419,14 @@ extern "C" int32_t bk_vec_norm2(bk_ctx* c, const double* x, int64_t n, double* o
   return BK_OK;
 }
 extern "C" int32_t bk_vec_norminf(bk_ctx* c, const double* x, int64_t n, double* out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   BK_DEVPTR(c, x);
   return bk_dev_norminf(c, x, n, out);
 }
 extern "C" int32_t bk_vec_diffdot(bk_ctx* c, const double* x, const double* x0, const double* tau, int64_t n, double* out) {
-  if (!c || !out) return BK_ERR_ARG;
+  BK_ENTER(c);
+  if (!out) return BK_ERR_ARG;
   BK_DEVPTR(c, x);
   BK_DEVPTR(c, x0);
   BK_DEVPTR(c, tau);

@@ -234,7 +234,7 @@ static __global__ void k_start_vector(double* v, long long n) {
 extern "C" int32_t bk_eigs_shift_invert(bk_ctx* c, double sigma, int32_t nev, int32_t krylovdim, double tol,
                                         int32_t maxrestart, const bk_gmres_opts* inner, const double* v0, double* vals_re,
                                         double* vals_im, double* vecs, int32_t* nconv, int32_t* nops) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   BK_CHECK(c, inner != nullptr && vals_re && vals_im, "null argument");
   const long long n = c->N;

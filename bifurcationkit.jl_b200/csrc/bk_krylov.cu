@@ -295,32 +295,22 @@ static size_t sh2_scratch_bytes(int E) { return sizeof(double) * (size_t)((BK2_R
     default: { constexpr int EE = 8; __VA_ARGS__; } break; \
   }
 
-template <typename K>
-static inline void bk2_ensure_smem(K kern, size_t bytes, size_t* cur) {
-  if (bytes > *cur) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    *cur = bytes;
-  }
-}
-
 static bool fused2_available(const OpDesc& op) { return op.kind == BK_SH2D && (op.nx % 2 == 0); }
 
 static int launch_fused2(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* w, int j, double* hcol) {
   const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
   Plan2 p = plan2(c, (long long)tiles_x * op.ny, sh2_scratch_bytes);
   p.grid = tiles_x * ((op.ny + p.E - 1) / p.E);
-  static size_t cur[BK2_EMAX + 1] = {0};
-  static size_t curb[BK2_EMAX + 1] = {0};
+  BK_CHECK(c, p.grid <= c->gmax, "partial-sum workspace too small for the fused grid");  // dots_finish indexes partials by CTA
   if (op.bordered) {
     BK2_DISPATCH(p.E, {
-      bk2_ensure_smem(k2_fused<EE, true>, p.smem, &curb[EE]);
+      bk_ensure_smem(c, k2_fused<EE, true>, p.smem);
       bk_launch_pdl(k2_fused<EE, true>, dim3(p.grid), dim3(BK2_THREADS), p.smem, c->stream, op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
                                                                      c->counters + 0, hcol, c->gcoef, p.NS, p.sred_off);
     });
   } else {
     BK2_DISPATCH(p.E, {
-      bk2_ensure_smem(k2_fused<EE, false>, p.smem, &cur[EE]);
+      bk_ensure_smem(c, k2_fused<EE, false>, p.smem);
       bk_launch_pdl(k2_fused<EE, false>, dim3(p.grid), dim3(BK2_THREADS), p.smem, c->stream, op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
                                                                       c->counters + 0, hcol, c->gcoef, p.NS, p.sred_off);
     });
@@ -348,22 +338,16 @@ static int launch_fused(bk_ctx* c, const OpDesc& op, const double* in, const dou
   size_t red = dots_smem(j);
   if (op.kind == BK_SH2D) {
     size_t sm = ShSmem<2>::BYTES > red ? ShSmem<2>::BYTES : red;
-    static size_t cur = 0;
-    if (sm > cur) {
-      cudaFuncSetAttribute(k_fused_jvp_dots<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      cur = sm;
-    }
+    bk_ensure_smem(c, k_fused_jvp_dots<2>, sm);
     int g = sh_num_tiles<2>(op.nx, op.ny, 1);
+    BK_CHECK(c, g <= c->gmax, "partial-sum workspace too small for the fused grid");
     k_fused_jvp_dots<2><<<g, BK_THREADS, sm, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
                                                           c->counters + 0, hcol, c->gcoef);
   } else {
     size_t sm = ShSmem<3>::BYTES > red ? ShSmem<3>::BYTES : red;
-    static size_t cur = 0;
-    if (sm > cur) {
-      cudaFuncSetAttribute(k_fused_jvp_dots<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      cur = sm;
-    }
+    bk_ensure_smem(c, k_fused_jvp_dots<3>, sm);
     int g = sh_num_tiles<3>(op.nx, op.ny, op.nz);
+    BK_CHECK(c, g <= c->gmax, "partial-sum workspace too small for the fused grid");
     k_fused_jvp_dots<3><<<g, BK_THREADS, sm, c->stream>>>(op, in, sp, w, c->V, c->ld, j, c->scales, c->partials,
                                                           c->counters + 0, hcol, c->gcoef);
   }
@@ -376,9 +360,8 @@ int bk_launch_dots(bk_ctx* c, const double* basis, const double* scales, const d
                    double* gcoef) {
   Plan2 p = plan2(c, (n + BK2_ROW - 1) / BK2_ROW, nullptr);
   BK_CHECK(c, p.grid <= c->gmax, "partial-sum workspace too small");
-  static size_t cur[BK2_EMAX + 1] = {0};
   BK2_DISPATCH(p.E, {
-    bk2_ensure_smem(k2_dots<EE>, p.smem, &cur[EE]);
+    bk_ensure_smem(c, k2_dots<EE>, p.smem);
     bk_launch_pdl(k2_dots<EE>, dim3(p.grid), dim3(BK2_THREADS), p.smem, c->stream, w, n, basis, c->ld, j, scales, c->partials, c->counters + 1, hcol,
                                                             gcoef, p.NS, p.sred_off);
   });
@@ -394,9 +377,8 @@ int bk_launch_update(bk_ctx* c, const double* basis, const double* gcoef, const 
                      double* h_out, double* scale_out) {
   Plan2 p = plan2(c, (n + BK2_ROW - 1) / BK2_ROW, nullptr);
   BK_CHECK(c, p.grid <= c->gmax, "partial-sum workspace too small");
-  static size_t cur[BK2_EMAX + 1] = {0};
   BK2_DISPATCH(p.E, {
-    bk2_ensure_smem(k2_update<EE>, p.smem, &cur[EE]);
+    bk_ensure_smem(c, k2_update<EE>, p.smem);
     bk_launch_pdl(k2_update<EE>, dim3(p.grid), dim3(BK2_THREADS), p.smem, c->stream, w, n, basis, c->ld, j, gcoef, vout, c->partials,
                                                               c->counters + 2, h_out, scale_out, p.NS);
   });
@@ -541,12 +523,29 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
   double tol = 0.0, res = 0.0;
   std::vector<double> H((size_t)(restart + 1) * restart), g(restart + 1), cs(restart), sn(restart), y(restart);
   bool first = true;
+  // Single-pass classical Gram-Schmidt (north_star) can lose orthogonality on long cycles / tight tolerances, and the
+  // Givens estimate |g[k+1]| then under-reports the residual (the reference's backend uses modified GS).  A cycle that ends
+  // "converged" after >= 40 Krylov vectors or with reltol < 1e-9 is therefore verified against the TRUE residual
+  // (one extra operator application); on failure the solve continues with CGS2 cycles from the current iterate.
+  bk_gmres_opts oo = *o;
+  o = &oo;
+  bool verify_pending = false;
   while (true) {
     double beta = 0;
     BK_TRY(init_residual(c, op, o, n, rhs, x, x_zero, &beta));
     if (first) {
       tol = fmax(o->reltol * beta, o->abstol);
       first = false;
+    }
+    if (verify_pending) {
+      verify_pending = false;
+      if (beta <= 4.0 * tol) {  // rounding slack between the Givens recurrence and the recomputed residual
+        res = beta;
+        conv = true;
+        break;
+      }
+      oo.orth = BK_ORTH_CGS2;
+      c->stats.cgs_fallbacks++;
     }
     res = beta;
     if (!(res > tol) || total >= maxiter || !(beta > 0.0)) {
@@ -620,6 +619,10 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
       x_zero = false;
     }
     conv = res <= tol;
+    if (conv && oo.orth == BK_ORTH_CGS && (k >= 40 || oo.reltol < 1e-9) && total < maxiter) {
+      verify_pending = true;
+      continue;
+    }
     if (conv || total >= maxiter || k == 0) break;
   }
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -654,7 +657,7 @@ static bk_gmres_opts default_opts() {
 
 extern "C" int32_t bk_gmres(bk_ctx* c, const double* rhs, double* x, double a0, double a1, const bk_gmres_opts* opts,
                             int32_t* converged, int32_t* iters, double* resnorm) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called before bk_gmres");
   bk_gmres_opts o = opts ? *opts : default_opts();
   double *drhs, *dx;

@@ -255,7 +255,7 @@ static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type) {
 }
 
 extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a1) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
   Precond& pc = c->pc;
   if (kind == BK_PC_NONE) {
@@ -551,7 +551,7 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
 }
 
 extern "C" int32_t bk_precond_apply(bk_ctx* c, const double* in, double* out) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   double *din, *dout;
   BK_TRY(bk_stage_in(c, in, c->N, 10, true, &din));
   BK_TRY(bk_stage_in(c, out, c->N, 11, false, &dout));

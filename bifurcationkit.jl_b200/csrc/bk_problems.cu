@@ -296,20 +296,12 @@ template <int MODE>
 static int launch_kind(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* out) {
   switch (op.kind) {
     case BK_SH2D: {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(k_sh_apply<2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ShSmem<2>::BYTES);
-        attr = true;
-      }
+      bk_ensure_smem(c, k_sh_apply<2, MODE>, ShSmem<2>::BYTES);
       k_sh_apply<2, MODE><<<sh_num_tiles<2>(op.nx, op.ny, 1), BK_THREADS, ShSmem<2>::BYTES, c->stream>>>(op, in, sp, out);
       break;
     }
     case BK_SH3D: {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(k_sh_apply<3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ShSmem<3>::BYTES);
-        attr = true;
-      }
+      bk_ensure_smem(c, k_sh_apply<3, MODE>, ShSmem<3>::BYTES);
       k_sh_apply<3, MODE><<<sh_num_tiles<3>(op.nx, op.ny, op.nz), BK_THREADS, ShSmem<3>::BYTES, c->stream>>>(op, in, sp, out);
       break;
     }
@@ -362,7 +354,7 @@ int bk_potrap_refresh_cache(bk_ctx* c) {
 
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" int32_t bk_residual(bk_ctx* c, const double* u, double* out) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   double *du, *dout;
   BK_TRY(bk_stage_in(c, u, c->N, 0, true, &du));
   BK_TRY(bk_stage_in(c, out, c->N, 1, false, &dout));
@@ -371,7 +363,7 @@ extern "C" int32_t bk_residual(bk_ctx* c, const double* u, double* out) {
 }
 
 extern "C" int32_t bk_jac_set_state(bk_ctx* c, const double* u) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, u != nullptr, "null state");
   cudaMemcpyKind kind = bk_is_device_ptr(u) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   BK_CUDA(c, cudaMemcpyAsync(c->u_state, u, 8 * (size_t)c->N, kind, c->stream));
@@ -382,7 +374,7 @@ extern "C" int32_t bk_jac_set_state(bk_ctx* c, const double* u) {
 }
 
 extern "C" int32_t bk_jvp(bk_ctx* c, const double* v, double* out, double a0, double a1) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called before bk_jvp");
   double *dv, *dout;
   BK_TRY(bk_stage_in(c, v, c->N, 0, true, &dv));
@@ -395,7 +387,7 @@ extern "C" int32_t bk_jvp(bk_ctx* c, const double* v, double* out, double a0, do
 
 extern "C" int32_t bk_bls_map(bk_ctx* c, const double* a, const double* b, double bc, int32_t has_shift, double shift,
                               double dotscale, const double* x, double* out) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   double *da, *db, *dx, *dout;
   BK_TRY(bk_stage_in(c, a, c->N, 2, true, &da));
@@ -414,7 +406,7 @@ extern "C" int32_t bk_bls_map(bk_ctx* c, const double* a, const double* b, doubl
 }
 
 extern "C" int32_t bk_potrap_set_section(bk_ctx* c, const double* phi, const double* xpi) {
-  if (!c) return BK_ERR_ARG;
+  BK_ENTER(c);
   BK_CHECK(c, c->kind == BK_POTRAP_CGL2D, "not a potrap context");
   long long n = c->N - 1;
   cudaMemcpyKind k1 = bk_is_device_ptr(phi) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

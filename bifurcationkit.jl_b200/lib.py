@@ -36,7 +36,8 @@ class GmresOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("last_fused_ms", C.c_double), ("last_fused_bytes", C.c_int64), ("last_fused_launches", C.c_int64),
-                ("total_fused_ms", C.c_double), ("total_fused_bytes", C.c_int64), ("total_fused_launches", C.c_int64)]
+                ("total_fused_ms", C.c_double), ("total_fused_bytes", C.c_int64), ("total_fused_launches", C.c_int64),
+                ("cgs_fallbacks", C.c_int64), ("total_precond_ms", C.c_double), ("total_precond_applies", C.c_int64)]
 
 
 class BK200Error(RuntimeError):

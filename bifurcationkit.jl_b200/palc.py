@@ -80,7 +80,9 @@ class V:
 
     @staticmethod
     def norminf(x):
-        return x.norminf() if isinstance(x, DeviceVec) else max(float(np.max(x)), -float(np.min(x)))  # = max|x|, no temporary
+        if isinstance(x, DeviceVec):
+            return x.norminf()  # NaN-propagating on the device (k_reduce MODE 1)
+        return nanmax2(float(np.max(x)), -float(np.min(x)))  # = max|x|, no temporary; NaN if any entry is NaN
 
     @staticmethod
     def zeros_like(x):
@@ -91,6 +93,12 @@ class V:
         y = V.host_alloc(len(x))
         y[...] = 0.0
         return y
+
+
+def nanmax2(a, b):
+    """max that propagates NaN like Julia's norm(x, Inf) / max: Python's max(0.0, nan) is 0.0, which would let a NaN
+    iterate pass `res < tol` as converged (the reference rejects the step, src/continuation/Palc.jl:228-231)."""
+    return max(a, b) if (a == a and b == b) else math.nan
 
 
 norminf = V.norminf
@@ -212,7 +220,7 @@ def newton_palc(prob, z0u, z0p, tau_u, tau_p, zpred_u, zpred_p, ds, theta, contp
     res_f = prob.F(x, p)
     res_n = Nfun(x, p)
     dFdp = V.zeros_like(x)
-    res = max(normN(res_f), abs(res_n))
+    res = nanmax2(normN(res_f), abs(res_n))
     residuals = [res]
     step = itlin = 0
     while step < opts.max_iterations and res > opts.tol:
@@ -225,7 +233,7 @@ def newton_palc(prob, z0u, z0p, tau_u, tau_p, zpred_u, zpred_p, ds, theta, contp
         p = min(max(p - up, contpar.p_min), contpar.p_max)
         res_f = prob.F(x, p, out=res_f)
         res_n = Nfun(x, p)
-        res = max(normN(res_f), abs(res_n))
+        res = nanmax2(normN(res_f), abs(res_n))
         residuals.append(res)
         step += 1
     return NonLinearSolution(x, p, residuals, residuals[-1] < opts.tol, step, itlin)

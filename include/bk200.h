@@ -78,6 +78,9 @@ typedef struct bk_stats {
   double  total_fused_ms;     /* cumulative over all solves that ran the FUSED JVP+Arnoldi kernel (timing enabled) */
   int64_t total_fused_bytes;  /* cumulative algorithmic bytes of those launches */
   int64_t total_fused_launches;
+  int64_t cgs_fallbacks;      /* solves whose single-pass CGS cycle failed the true-residual check and continued with CGS2 */
+  double  total_precond_ms;   /* cumulative device time of preconditioner applications inside bk_gmres (timing enabled) */
+  int64_t total_precond_applies;
 } bk_stats;
 
 /* ---- context --------------------------------------------------------------------------- */

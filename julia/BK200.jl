@@ -39,7 +39,13 @@ mutable struct Context
                    device, KINDS[kind], d, L, krylov_m, h)
         st < 0 && error("bk_ctx_create: " * unsafe_string(ccall((:bk_last_error, lib), Cstring, (Ptr{Cvoid},), h[])))
         c = new(h[], Int(ccall((:bk_problem_size, lib), Int64, (Ptr{Cvoid},), h[])))
-        finalizer(x -> ccall((:bk_ctx_destroy, lib), Int32, (Ptr{Cvoid},), x.handle), c)
+        # bk_ctx_destroy frees every vector still alive (vec_live); the handle is nulled so that DeviceVec finalizers
+        # running AFTER this one (finalizer order is unspecified for objects that die together) do not touch a freed ctx
+        finalizer(c) do x
+            h = x.handle
+            x.handle = C_NULL
+            h == C_NULL || ccall((:bk_ctx_destroy, lib), Int32, (Ptr{Cvoid},), h)
+        end
     end
 end
 check(c::Context, st) = st < 0 ? error(unsafe_string(ccall((:bk_last_error, lib), Cstring, (Ptr{Cvoid},), c.handle))) : st
@@ -56,7 +62,9 @@ mutable struct DeviceVec
         p = Ref{Ptr{Float64}}(C_NULL)
         check(ctx, ccall((:bk_vec_alloc, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Ptr{Float64}}), ctx.handle, n, p))
         v = new(ctx, p[], n)
-        finalizer(x -> ccall((:bk_vec_free, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), x.ctx.handle, x.ptr), v)
+        finalizer(v) do x
+            x.ctx.handle == C_NULL || ccall((:bk_vec_free, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), x.ctx.handle, x.ptr)
+        end
     end
 end
 DeviceVec(ctx::Context, a::Vector{Float64}) = (v = DeviceVec(ctx, length(a)); ccall((:bk_vec_upload, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.handle, v.ptr, a, length(a)); v)
