@@ -32,22 +32,39 @@ struct OpDesc {
   const double* fcache;  // F(x_i) cache, M slices (device)
 };
 
+// general-length transform plan (bk_fft_gen.cuh), passed by value to the kernels
+namespace bkg {
+#define BKG_MAXPASS 16
+struct Plan {
+  int n;                   // line length
+  int L;                   // FFT length: 2n (DCT-II, even extension) or 2n + 2 (DST-I, odd extension)
+  int npass;
+  int radix[BKG_MAXPASS];  // Stockham radices (prime factors of L, 4 preferred over 2 x 2)
+  const double2* wl;       // W_L^t = exp(-2 pi i t / L), t < L
+  const double2* ph;       // exp(-i pi k / 2n), k < n (DCT-II pre/post twiddle)
+  double dst_scale;        // sqrt(2 / (n + 1)) / 2
+};
+}  // namespace bkg
+
 struct Precond {
   int kind = BK_PC_NONE;
   double a0 = 0, a1 = 0;
-  // DCT/DST tables (device)
-  double2* tw[3] = {nullptr, nullptr, nullptr};     // FFT twiddles exp(-2 pi i k/n), k < n/2
-  double2* dtw[3] = {nullptr, nullptr, nullptr};    // DCT twiddles exp(-i pi k/(2n)), k <= n/2
-  double2* wn[3] = {nullptr, nullptr, nullptr};     // real-FFT unpack twiddles exp(-2 pi i k/n), k <= n/2
-  double* lam[3] = {nullptr, nullptr, nullptr};     // 1-D eigenvalues of the Laplacian factors
-  double* dense[3] = {nullptr, nullptr, nullptr};   // dense transform matrices for non power-of-two sizes (n x n, forward)
-  int pow2[3] = {0, 0, 0};
+  double* lam[3] = {nullptr, nullptr, nullptr};     // 1-D eigenvalues of the Laplacian factors (natural order)
+  int ttype[3] = {0, 0, 0};                         // 0: DCT-II (Neumann), 1: DST-I (Dirichlet)
+  // register-resident power-of-two kernels (bk_fft_fast.cuh): log2(n) or 0, and their tables
+  int fast[3] = {0, 0, 0};
+  double2* ftw[3] = {nullptr, nullptr, nullptr};    // per-pass contiguous FFT twiddles
+  double2* fom[3] = {nullptr, nullptr, nullptr};    // w_k = exp(-i pi k / 2n), register-major
+  double2* flam2[3] = {nullptr, nullptr, nullptr};  // (lambda[k], lambda[n-k]), register-major
+  // general lengths (bk_fft_gen.cuh)
+  bkg::Plan gplan[3] = {};
+  double2* gwl[3] = {nullptr, nullptr, nullptr};
+  double2* gph[3] = {nullptr, nullptr, nullptr};
   double* work = nullptr;                           // scratch vector (N)
   double* work2 = nullptr;
   // chan tridiagonal LU factors
   double* tri = nullptr;
   // potrap circulant preconditioner
-  void* blas = nullptr;      // cublasHandle_t
   double2* tdft = nullptr;   // exp(-2 pi i j / (M-1))
   double po_r = 0, po_nu = 0, po_T = 0;
 };
@@ -109,6 +126,8 @@ struct bk_ctx {
   bool timing = false;
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tpairs;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pc_pairs;  // one pair per preconditioner application (timing enabled)
+  size_t pc_pairs_used = 0;
   // cudaFuncAttributeMaxDynamicSharedMemorySize already granted per kernel ON THIS CONTEXT'S DEVICE (the attribute is per
   // device: a process-wide cache would leave a second GPU's copy of the kernel at the 48 KB default)
   std::unordered_map<const void*, size_t> smem_attr;
@@ -155,6 +174,7 @@ int bk_launch_apply(bk_ctx* c, const OpDesc& op, const double* in_dev, const dou
 int bk_potrap_refresh_cache(bk_ctx* c);
 
 int bk_precond_apply_dev(bk_ctx* c, const double* in_dev, double* out_dev, long long n);
+void bk_harvest_pc_timing(bk_ctx* c);
 
 // vector kernels (device pointers)
 int bk_dev_axpby(bk_ctx* c, double* y, double a, const double* x, double b, long long n);

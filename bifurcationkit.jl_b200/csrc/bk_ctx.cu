@@ -153,11 +153,13 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
   for (double* b : bufs)
     if (b) cudaFree(b);
   for (int d = 0; d < 3; ++d) {
-    if (c->pc.tw[d]) cudaFree(c->pc.tw[d]);
-    if (c->pc.dtw[d]) cudaFree(c->pc.dtw[d]);
-    if (c->pc.wn[d]) cudaFree(c->pc.wn[d]);
-    if (c->pc.lam[d]) cudaFree(c->pc.lam[d]);
-    if (c->pc.dense[d]) cudaFree(c->pc.dense[d]);
+    void* tabs[] = {c->pc.lam[d], c->pc.ftw[d], c->pc.fom[d], c->pc.flam2[d], c->pc.gwl[d], c->pc.gph[d]};
+    for (void* t : tabs)
+      if (t) cudaFree(t);
+  }
+  for (auto& p : c->pc_pairs) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
   }
   if (c->pc.tdft) cudaFree(c->pc.tdft);
   if (c->counters) cudaFree(c->counters);
@@ -192,9 +194,25 @@ extern "C" int32_t bk_set_params(bk_ctx* c, const double* p, int32_t n) {
   for (int i = 0; i < n; ++i) c->par[i] = p[i];
   return BK_OK;
 }
+// sum the per-application event pairs recorded by bk_precond_apply_dev (timing enabled); the stream must be idle
+void bk_harvest_pc_timing(bk_ctx* c) {
+  for (size_t i = 0; i < c->pc_pairs_used; ++i) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, c->pc_pairs[i].first, c->pc_pairs[i].second) == cudaSuccess) {
+      c->stats.total_precond_ms += t;
+      c->stats.total_precond_applies++;
+    }
+  }
+  c->pc_pairs_used = 0;
+}
+
 extern "C" int32_t bk_get_stats(bk_ctx* c, bk_stats* out) {
   BK_ENTER(c);
   if (!out) return BK_ERR_ARG;
+  if (c->pc_pairs_used) {
+    BK_CUDA(c, cudaStreamSynchronize(c->stream));
+    bk_harvest_pc_timing(c);
+  }
   *out = c->stats;
   return BK_OK;
 }

@@ -626,6 +626,7 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
     if (conv || total >= maxiter || k == 0) break;
   }
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->pc_pairs_used) bk_harvest_pc_timing(c);
   if (c->timing) {
     double ms = 0;
     for (size_t i = 0; i < timer_slot && i < c->tpairs.size(); ++i) {

@@ -6,100 +6,37 @@
 //   Neumann-closure Laplacian (SH2d-fronts.jl:13-29) is diagonalised by the DCT-II, so
 //   (L1 + shift I)^-1 r = IDCT( DCT(r) / ((1 + lx_i + ly_j [+ lz_k])^2 + shift) )  exactly
 //   (identity pinned in tests/test_oracle_palc.py::test_dct_symbol_diagonalises_L1).
-//   Each 1-D DCT of a power-of-two length is a shared-memory radix-2 complex FFT (Makhoul's
-//   reordering: v[m] = x[2m], v[n-1-m] = x[2m+1]; C[k] = Re(e^{-i pi k/2n} FFT(v)[k])); other lengths
-//   use a dense n x n transform.  Lines along x are contiguous; lines along y/z are processed in
-//   batches of W consecutive x so every global access stays coalesced.
+//   Power-of-two line lengths 64..2048 run the register-resident FFT kernels of bk_fft_fast.cuh (two lines per complex
+//   FFT, the last dimension fused: forward + symbol + inverse, so an application is 3 kernels in 2-D and 5 in 3-D);
+//   every other length runs the mixed-radix kernel of bk_fft_gen.cuh.  No library on this path.
 // BK_PC_CHAN_TRIDIAG: lu(P) of examples/chan.jl:108-111 (Thomas algorithm, one thread: n = 1e3 plumbing).
-// BK_PC_CGL_DST: per-component (a0 I + a1 Lap_dirichlet)^-1 by dense DST-I (stand-in for the ILU of
+// BK_PC_CGL_DST: per-component (a0 I + a1 Lap_dirichlet)^-1 by DST-I (stand-in for the ILU of
 //   examples/cGL2d.jl:209-213); for potrap contexts it is applied slice by slice (block Jacobi, cf.
 //   jacobian_block_diag, src/periodicorbit/PeriodicOrbitTrapeze.jl:619-643).
+// BK_PC_POTRAP_CIRC: block-circulant-in-time linearisation of the Trapeze functional at the trivial state, inverted
+//   exactly: DST-I in space, u1 +- i u2, DFT over the M-1 cyclic slices, scalar symbol.
 #include <cmath>
 #include <cstdlib>
 #include <utility>
 #include <vector>
-#include <cublas_v2.h>
 #include "bk_common.cuh"
 
-#include "bk_dct.cuh"
-#include "bk_dct2.cuh"
+#include "bk_fft_fast.cuh"
+#include "bk_fft_gen.cuh"
 
-// Opt-in second version of the DCT kernels (bk_dct2.cuh; BK_DCT_V2=1).  Returns false when (n, W) has no instantiation.
-template <int LOGM, int LOGW>
-static bool launch_dct_v2(bk_ctx* c, int d, int mode, const double* in, double* out, const LineGeom& g, int nthr, const DctTables& tb,
-                          const SymbolArgs& sy) {
-  constexpr int W = 1 << LOGW;
-  const size_t sm = 16 * ((size_t)Dct2Cfg<LOGM>::MP * W + Dct2Cfg<LOGM>::TWN) + (mode == 2 ? 8 * (size_t)Dct2Cfg<LOGM>::N * W : 0);
-  static bool attr = false;
-  if (!attr) {
-    const int mx = 160 * 1024;
-    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_dct2v2<LOGM, LOGW, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    attr = true;
-  }
-  if (d == 0) {
-    dim3 grid((g.nouter + W - 1) / W);
-    if (mode == 0)
-      bk_launch_pdl(k_dct2v2<LOGM, LOGW, false, 0>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
-    else if (mode == 1)
-      bk_launch_pdl(k_dct2v2<LOGM, LOGW, false, 1>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
-    else
-      return false;
-  } else {
-    dim3 grid((g.nx + W - 1) / W, g.nouter);
-    if (mode == 0)
-      bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 0>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
-    else if (mode == 1)
-      bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 1>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
-    else
-      bk_launch_pdl(k_dct2v2<LOGM, LOGW, true, 2>, grid, dim3(nthr), sm, c->stream, in, out, g, tb, sy);
-  }
-  return true;
-}
-static bool try_dct_v2(bk_ctx* c, int d, int mode, const double* in, double* out, const LineGeom& g, int W, int nthr, const DctTables& tb,
-                       const SymbolArgs& sy) {
-  static int on = -1;
-  if (on < 0) on = getenv("BK_DCT_V2") ? 1 : 0;
-  if (!on || nthr > 512) return false;
-  if (g.n == 2048 && W == 2) return launch_dct_v2<10, 1>(c, d, mode, in, out, g, nthr, tb, sy);
-  if (g.n == 1024 && W == 4) return launch_dct_v2<9, 2>(c, d, mode, in, out, g, nthr, tb, sy);
-  if (g.n == 1024 && W == 2) return launch_dct_v2<9, 1>(c, d, mode, in, out, g, nthr, tb, sy);
-  if (g.n == 512 && W == 8) return launch_dct_v2<8, 3>(c, d, mode, in, out, g, nthr, tb, sy);
-  if (g.n == 512 && W == 4) return launch_dct_v2<8, 2>(c, d, mode, in, out, g, nthr, tb, sy);
-  if (g.n == 256 && W == 16) return launch_dct_v2<7, 4>(c, d, mode, in, out, g, nthr, tb, sy);
-  if (g.n == 256 && W == 8) return launch_dct_v2<7, 3>(c, d, mode, in, out, g, nthr, tb, sy);
-  return false;
-}
-
-// dense transform of every line: out[line, k] = sum_e M[k*n + e] in[line, e]
-static __global__ void __launch_bounds__(256) k_dense_lines(const double* __restrict__ in, double* __restrict__ out, LineGeom g,
-                                                            const double* __restrict__ M) {
-  const long long nlines = (long long)g.nx * g.nouter;
-  const long long total = nlines * g.n;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    long long line = q % nlines;
-    int k = (int)(q / nlines);
-    long long x = line % g.nx, o = line / g.nx;
-    long long base = x + o * g.os;
-    const double* Mk = M + (long long)k * g.n;
-    double acc = 0.0;
-    for (int e = 0; e < g.n; ++e) acc = fma(__ldg(Mk + e), in[base + (long long)e * g.es], acc);
-    out[base + (long long)k * g.es] = acc;
-  }
-}
+#ifndef BK_FFT_LOGE
+#define BK_FFT_LOGE 5   // complex values per thread of the fast kernels: 2^5 = 32 (n = 1024 = 32 x 32: one exchange per FFT)
+#endif
 
 // divide by the symbol
 static __global__ void __launch_bounds__(256) k_sh_symbol_div(double* __restrict__ a, int nx, int ny, int nz,
                                                               const double* __restrict__ lx, const double* __restrict__ ly,
-                                                              const double* __restrict__ lz, double shift) {
+                                                              const double* __restrict__ lz, double shift, double scale) {
   const long long total = (long long)nx * ny * nz;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
     int i = (int)(q % nx), j = (int)((q / nx) % ny), k = (int)(q / ((long long)nx * ny));
     double t = 1.0 + lx[i] + ly[j] + (lz ? lz[k] : 0.0);
-    a[q] = a[q] / (t * t + shift);
+    a[q] = a[q] * scale / (t * t + shift);
   }
 }
 static __global__ void __launch_bounds__(256) k_helmholtz_symbol_div(double* __restrict__ a, int nx, int ny, long long nblocks,
@@ -195,12 +132,6 @@ static __global__ void k_thomas(const double* __restrict__ tri, const double* __
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static bool is_pow2(long long n) { return n >= 16 && n <= 4096 && (n & (n - 1)) == 0; }
-static int ilog2(long long n) {
-  int l = 0;
-  while ((1LL << l) < n) ++l;
-  return l;
-}
 static inline int lin_grid(bk_ctx* c, long long n) {
   long long g = (n + 255) / 256, cap = (long long)c->nsm * 8;
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
@@ -208,13 +139,153 @@ static inline int lin_grid(bk_ctx* c, long long n) {
 
 static int upload(bk_ctx* c, void** dst, const void* src, size_t bytes) {
   if (*dst) cudaFree(*dst);
+  *dst = nullptr;
   BK_CUDA(c, cudaMalloc(dst, bytes));
   BK_CUDA(c, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
   return BK_OK;
 }
 
-// transform tables for dimension d of length n. type 0: DCT-II (Neumann), 1: DST-I (Dirichlet; dense only)
-static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type) {
+// ---- fast path: one instantiation per line length -------------------------------------------------------------------------
+static int fast_logn(long long n) {
+  static int off = -1;
+  if (off < 0) off = getenv("BK_FFT_NO_FAST") ? 1 : 0;  // diagnostics: force the general kernel everywhere
+  if (off) return 0;
+  for (int l = BK_FFT_LOGE + 1; l <= 11; ++l)
+    if (n == (1LL << l)) return l;
+  return 0;
+}
+#define BKF_DISPATCH(LOGN, ...)                                                        \
+  switch (LOGN) {                                                                      \
+    case 6: { using FC = bkf::Cfg<6, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
+    case 7: { using FC = bkf::Cfg<7, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
+    case 8: { using FC = bkf::Cfg<8, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
+    case 9: { using FC = bkf::Cfg<9, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
+    case 10: { using FC = bkf::Cfg<10, BK_FFT_LOGE>; __VA_ARGS__; } break;             \
+    default: { using FC = bkf::Cfg<11, BK_FFT_LOGE>; __VA_ARGS__; } break;             \
+  }
+
+template <class FC>
+static int fast_setup(bk_ctx* c, int d, const double* lam_host) {
+  std::vector<double> tw, om, lam2;
+  bkf::build_tables<FC>(tw, om, lam2, lam_host);
+  Precond& pc = c->pc;
+  if (tw.empty()) tw.assign(2, 0.0);
+  BK_TRY(upload(c, (void**)&pc.ftw[d], tw.data(), 8 * tw.size()));
+  BK_TRY(upload(c, (void**)&pc.fom[d], om.data(), 8 * om.size()));
+  BK_TRY(upload(c, (void**)&pc.flam2[d], lam2.data(), 8 * lam2.size()));
+  return BK_OK;
+}
+
+// mode 0 forward (2 C), 1 inverse (n x), 2 fused forward + symbol + inverse (strided only)
+template <class FC>
+static int fast_launch(bk_ctx* c, int d, bool strided, int mode, const double* in, double* out, const bkf::Geom& g,
+                       const bkf::Symbol* sy) {
+  Precond& pc = c->pc;
+  bkf::Tables tb{pc.ftw[d], pc.fom[d], pc.flam2[d]};
+  bkf::Symbol s0{};
+  if (sy) s0 = *sy;
+  if (strided) {
+    dim3 grid((g.nb + 2 * FC::PP - 1) / (2 * FC::PP), g.nouter);
+    if (mode == 0) {
+      bk_ensure_smem(c, bkf::k_strided<FC, 0>, FC::SMEM);
+      BK_CUDA(c, bk_launch_pdl(bkf::k_strided<FC, 0>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb, s0));
+    } else if (mode == 1) {
+      bk_ensure_smem(c, bkf::k_strided<FC, 1>, FC::SMEM);
+      BK_CUDA(c, bk_launch_pdl(bkf::k_strided<FC, 1>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb, s0));
+    } else {
+      bk_ensure_smem(c, bkf::k_strided<FC, 2>, FC::SMEM);
+      BK_CUDA(c, bk_launch_pdl(bkf::k_strided<FC, 2>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb, s0));
+    }
+  } else {
+    dim3 grid((unsigned)((g.nb + 2 * FC::PP - 1) / (2 * FC::PP)));
+    if (mode == 0) {
+      bk_ensure_smem(c, bkf::k_contig<FC, 0>, FC::SMEM);
+      BK_CUDA(c, bk_launch_pdl(bkf::k_contig<FC, 0>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb));
+    } else {
+      bk_ensure_smem(c, bkf::k_contig<FC, 1>, FC::SMEM);
+      BK_CUDA(c, bk_launch_pdl(bkf::k_contig<FC, 1>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb));
+    }
+  }
+  return BK_OK;
+}
+
+// ---- general path ----------------------------------------------------------------------------------------------------------
+static void factorize(int L, bkg::Plan& pl) {
+  pl.npass = 0;
+  while (L % 4 == 0 && pl.npass < BKG_MAXPASS) {
+    pl.radix[pl.npass++] = 4;
+    L /= 4;
+  }
+  for (int p = 2; L > 1 && pl.npass < BKG_MAXPASS; ++p)
+    while (L % p == 0 && pl.npass < BKG_MAXPASS) {
+      pl.radix[pl.npass++] = p;
+      L /= p;
+    }
+}
+#define BKG_THREADS 512
+#define BKG_SMEM_BUDGET (100 * 1024)   // two CTAs per SM
+#define BKG_SMEM_MAX (200 * 1024)
+static int gen_ppg(int L) {
+  long long per = 32LL * L;  // two buffers of L complex values per pair
+  int p = (int)(BKG_SMEM_BUDGET / per);
+  if (p < 1) p = 1;
+  if (p > 8) p = 8;
+  return p;
+}
+
+// type 0: DCT-II (Neumann), 1: DST-I (Dirichlet)
+static int gen_setup(bk_ctx* c, int d, int n, int type) {
+  Precond& pc = c->pc;
+  bkg::Plan& pl = pc.gplan[d];
+  pl.n = n;
+  pl.L = type == 0 ? 2 * n : 2 * n + 2;
+  BK_CHECK(c, 32LL * pl.L <= BKG_SMEM_MAX, "line too long for the general transform kernel (n <= 3199)");
+  factorize(pl.L, pl);
+  const long double PI = 3.14159265358979323846264338327950288L;
+  std::vector<double> wl(2 * (size_t)pl.L), ph(2 * (size_t)n);
+  for (int t = 0; t < pl.L; ++t) {
+    wl[2 * t] = (double)cosl(-2.0L * PI * t / pl.L);
+    wl[2 * t + 1] = (double)sinl(-2.0L * PI * t / pl.L);
+  }
+  for (int k = 0; k < n; ++k) {
+    ph[2 * k] = (double)cosl(-PI * k / (2.0L * n));
+    ph[2 * k + 1] = (double)sinl(-PI * k / (2.0L * n));
+  }
+  BK_TRY(upload(c, (void**)&pc.gwl[d], wl.data(), 8 * wl.size()));
+  BK_TRY(upload(c, (void**)&pc.gph[d], ph.data(), 8 * ph.size()));
+  pl.wl = pc.gwl[d];
+  pl.ph = pc.gph[d];
+  pl.dst_scale = 0.5 * sqrt(2.0 / (n + 1.0));
+  return BK_OK;
+}
+
+// mode 0 DCT forward (2 C), 1 DCT inverse (n x), 2 DST-I (orthonormal)
+static int gen_launch(bk_ctx* c, int d, bool strided, int mode, const double* in, double* out, const bkf::Geom& g) {
+  const bkg::Plan& pl = c->pc.gplan[d];
+  const int ppg = gen_ppg(pl.L);
+  const size_t sm = 32 * (size_t)pl.L * ppg;
+  const long long npairs = ((long long)g.nb + 1) / 2;
+  dim3 grid((unsigned)((npairs + ppg - 1) / ppg), strided ? g.nouter : 1);
+#define BKG_GO(S, M)                                                                                                       \
+  do {                                                                                                                     \
+    bk_ensure_smem(c, bkg::k_gen<S, M>, sm);                                                                               \
+    BK_CUDA(c, bk_launch_pdl(bkg::k_gen<S, M>, grid, dim3(BKG_THREADS), sm, c->stream, in, out, g, pl, ppg));              \
+  } while (0)
+  if (strided) {
+    if (mode == 0) BKG_GO(true, 0);
+    else if (mode == 1) BKG_GO(true, 1);
+    else BKG_GO(true, 2);
+  } else {
+    if (mode == 0) BKG_GO(false, 0);
+    else if (mode == 1) BKG_GO(false, 1);
+    else BKG_GO(false, 2);
+  }
+#undef BKG_GO
+  return BK_OK;
+}
+
+// transform tables for dimension d of length n. type 0: DCT-II (Neumann), 1: DST-I (Dirichlet)
+static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type, bool even_nx) {
   Precond& pc = c->pc;
   std::vector<double> lam(n);
   const long double PI = 3.14159265358979323846264338327950288L;
@@ -222,36 +293,12 @@ static int setup_dim(bk_ctx* c, int d, long long n, double inv_h2, int type) {
     lam[k] = (type == 0) ? (double)((2.0L * cosl(PI * k / n) - 2.0L)) * inv_h2
                          : (double)(-(2.0L - 2.0L * cosl(PI * (k + 1) / (n + 1)))) * inv_h2;
   BK_TRY(upload(c, (void**)&pc.lam[d], lam.data(), 8 * n));
-  pc.pow2[d] = (type == 0 && is_pow2(n)) ? 1 : 0;
-  if (pc.pow2[d]) {
-    const long long M = n / 2;
-    std::vector<double2> tw(M / 2), wn(M + 1), dtw(M + 1);
-    for (long long k = 0; k < M / 2; ++k) tw[k] = make_double2((double)cosl(-2.0L * PI * k / M), (double)sinl(-2.0L * PI * k / M));
-    for (long long k = 0; k <= M; ++k) {
-      wn[k] = make_double2((double)cosl(-2.0L * PI * k / n), (double)sinl(-2.0L * PI * k / n));
-      dtw[k] = make_double2((double)cosl(-PI * k / (2.0L * n)), (double)sinl(-PI * k / (2.0L * n)));
-    }
-    BK_TRY(upload(c, (void**)&pc.tw[d], tw.data(), 16 * (M / 2)));
-    BK_TRY(upload(c, (void**)&pc.wn[d], wn.data(), 16 * (M + 1)));
-    BK_TRY(upload(c, (void**)&pc.dtw[d], dtw.data(), 16 * (M + 1)));
-  } else {
-    // dense forward F (n x n) followed by dense inverse Finv (n x n)
-    std::vector<double> M(2 * n * n);
-    for (long long k = 0; k < n; ++k)
-      for (long long e = 0; e < n; ++e) {
-        if (type == 0) {
-          long double cv = cosl(PI * (2 * e + 1) * k / (2.0L * n));
-          M[k * n + e] = (double)cv;                                        // C[k] = sum_e x[e] cos(pi (2e+1) k / 2n)
-          M[n * n + e * n + k] = (double)((k == 0 ? 1.0L : 2.0L) * cv / n);  // x[e] = (C0 + 2 sum_k>0 C[k] cos)/n
-        } else {
-          long double sv = sinl(PI * (e + 1) * (k + 1) / (n + 1.0L)) * sqrtl(2.0L / (n + 1.0L));
-          M[k * n + e] = (double)sv;  // orthonormal DST-I is its own inverse
-          M[n * n + e * n + k] = (double)sv;
-        }
-      }
-    BK_TRY(upload(c, (void**)&pc.dense[d], M.data(), 8 * 2 * n * n));
+  pc.ttype[d] = type;
+  pc.fast[d] = (type == 0 && even_nx) ? fast_logn(n) : 0;  // 16-byte accesses need an even row length
+  if (pc.fast[d]) {
+    BKF_DISPATCH(pc.fast[d], BK_TRY(fast_setup<FC>(c, d, lam.data())));
   }
-  return BK_OK;
+  return gen_setup(c, d, (int)n, type);  // always available: unaligned vectors fall back to it
 }
 
 extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a1) {
@@ -264,24 +311,19 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
   }
   if (!pc.work) BK_CUDA(c, cudaMalloc(&pc.work, 8 * (size_t)c->ld));
   if (!pc.work2) BK_CUDA(c, cudaMalloc(&pc.work2, 8 * (size_t)c->ld));
+  const bool even_nx = (c->dims[0] % 2) == 0;
   if (kind == BK_PC_SH_DCT) {
     BK_CHECK(c, c->kind == BK_SH2D || c->kind == BK_SH3D, "BK_PC_SH_DCT needs a Swift-Hohenberg context");
     int nd = c->kind == BK_SH3D ? 3 : 2;
     for (int d = 0; d < nd; ++d) {
       double h = 2 * c->lengths[d] / c->dims[d];
-      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 0));
+      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 0, even_nx));
     }
   } else if (kind == BK_PC_CGL_DST) {
     BK_CHECK(c, c->kind == BK_CGL2D || c->kind == BK_POTRAP_CGL2D, "BK_PC_CGL_DST needs a cGL context");
     for (int d = 0; d < 2; ++d) {
       double h = 2 * c->lengths[d] / c->dims[d];
-      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1));
-    }
-    if (getenv("BK_CGL_DST_GEMM") && !pc.blas) {  // opt-in: dense DST-I through cuBLAS instead of k_dense_lines (see apply)
-      cublasHandle_t hnd;
-      BK_CHECK(c, cublasCreate(&hnd) == CUBLAS_STATUS_SUCCESS, "cublasCreate failed");
-      cublasSetStream(hnd, c->stream);
-      pc.blas = (void*)hnd;
+      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1, even_nx));
     }
   } else if (kind == BK_PC_POTRAP_CIRC) {
     BK_CHECK(c, c->kind == BK_POTRAP_CGL2D, "BK_PC_POTRAP_CIRC needs a Trapeze (potrap) context");
@@ -290,18 +332,12 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
     BK_CHECK(c, a0 > 0, "BK_PC_POTRAP_CIRC: a0 must be the period T > 0");
     for (int d = 0; d < 2; ++d) {
       double h = 2 * c->lengths[d] / c->dims[d];
-      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1));
+      BK_TRY(setup_dim(c, d, c->dims[d], 1.0 / (h * h), 1, even_nx));
     }
     std::vector<double2> tw(K);
     const long double PI = 3.14159265358979323846264338327950288L;
     for (int j = 0; j < K; ++j) tw[j] = make_double2((double)cosl(-2.0L * PI * j / K), (double)sinl(-2.0L * PI * j / K));
     BK_TRY(upload(c, (void**)&pc.tdft, tw.data(), 16 * (size_t)K));
-    if (!pc.blas) {
-      cublasHandle_t hnd;
-      BK_CHECK(c, cublasCreate(&hnd) == CUBLAS_STATUS_SUCCESS, "cublasCreate failed");
-      cublasSetStream(hnd, c->stream);
-      pc.blas = (void*)hnd;
-    }
     pc.po_T = a0;
     pc.po_r = c->par[0];   // (r, mu, nu, c3, c5)
     pc.po_nu = c->par[2];
@@ -336,94 +372,41 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
   return BK_OK;
 }
 
-// one 1-D transform pass along dimension d over `nblocks` consecutive blocks of nx*ny(*nz) values
-static int transform_pass(bk_ctx* c, int d, int dir, const double* in, double* out, int nx, int ny, int nz,
-                          const SymbolArgs* fused_sym = nullptr) {
+// one 1-D transform pass along dimension d over fields of nx * ny * nz values.
+// mode 0: forward, 1: inverse; fused != NULL (fast path, last dimension): forward + symbol + inverse in one kernel.
+// Conventions: DCT forward returns 2 C, DCT inverse returns n x (the caller's symbol carries 1 / prod(2 n_d)); DST-I is orthonormal.
+static int transform_pass(bk_ctx* c, int d, int mode, const double* in, double* out, int nx, int ny, int nz, bool aligned,
+                          const bkf::Symbol* fused = nullptr) {
   Precond& pc = c->pc;
-  LineGeom g;
-  const int dims[3] = {nx, ny, nz};
-  g.n = dims[d];
+  bkf::Geom g;
+  bool strided = d != 0;
   if (d == 0) {
     g.es = 1;
-    g.nx = 1;
     g.os = nx;
-    g.nouter = ny * nz;
+    g.nb = ny * nz;  // number of lines
+    g.nouter = 1;
   } else if (d == 1) {
     g.es = nx;
-    g.nx = nx;
+    g.nb = nx;
     g.os = (long long)nx * ny;
     g.nouter = nz;
   } else {
     g.es = (long long)nx * ny;
-    g.nx = nx;
+    g.nb = nx;
     g.os = nx;
     g.nouter = ny;
   }
-  if (pc.pow2[d]) {
-    static int env_w = -1, env_t = -1;
-    if (env_w < 0) {
-      const char* a = getenv("BK_DCT_W");
-      const char* b = getenv("BK_DCT_THREADS");
-      env_w = a ? atoi(a) : 0;
-      env_t = b ? atoi(b) : 0;
-    }
-    int W = 4096 / g.n;
-    if (W < 1) W = 1;
-    if (W > 16) W = 16;
-    if (env_w > 0) W = env_w;
-    while (W & (W - 1)) W &= W - 1;  // power of two (shift/mask indexing in the kernels)
-    const int nthr = env_t > 0 ? env_t : 512;
-    const int mode = fused_sym ? 2 : (dir > 0 ? 0 : 1);
-    size_t sm = sizeof(double2) * (size_t)DCT_PADDED(g.n / 2) * W + (mode == 2 ? sizeof(double) * (size_t)g.n * W : 0);
-    int logM = ilog2(g.n / 2);
-    DctTables tb{pc.tw[d], pc.wn[d], pc.dtw[d]};
-    SymbolArgs sy{nullptr, nullptr, nullptr, 0.0, nullptr, nullptr, 0};
-    if (fused_sym) sy = *fused_sym;
-    if (try_dct_v2(c, d, mode, in, out, g, W, nthr, tb, sy)) {
-      c->stats.kernel_launches++;
-      BK_CUDA(c, cudaGetLastError());
-      return BK_OK;
-    }
-    static bool attr = false;
-    if (!attr) {
-      const int mx = 160 * 1024;
-      cudaFuncSetAttribute(k_dct2<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      cudaFuncSetAttribute(k_dct2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      cudaFuncSetAttribute(k_dct2<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      cudaFuncSetAttribute(k_dct2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      cudaFuncSetAttribute(k_dct2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      attr = true;
-    }
-    if (d == 0) {
-      int grid = (g.nouter + W - 1) / W;
-      if (mode == 0)
-        bk_launch_pdl(k_dct2<false, 0>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
-      else
-        bk_launch_pdl(k_dct2<false, 1>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
-    } else {
-      dim3 grid((g.nx + W - 1) / W, g.nouter);
-      if (mode == 0)
-        bk_launch_pdl(k_dct2<true, 0>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
-      else if (mode == 1)
-        bk_launch_pdl(k_dct2<true, 1>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
-      else
-        bk_launch_pdl(k_dct2<true, 2>, dim3(grid), dim3(nthr), sm, c->stream, in, out, g, logM, W, ilog2(W), tb, sy);
-    }
+  if (pc.fast[d] && aligned) {
+    BKF_DISPATCH(pc.fast[d], BK_TRY(fast_launch<FC>(c, d, strided, fused ? 2 : mode, in, out, g, fused)));
   } else {
-    const double* M = pc.dense[d] + (dir > 0 ? 0 : (size_t)g.n * g.n);
-    LineGeom gg = g;
-    if (d == 0) {  // express x-lines in the (x, outer) form used by the dense kernel: x index is the line element
-      gg.nx = 1;
-      gg.os = nx;
-      gg.nouter = ny * nz;
-    }
-    long long total = (long long)nx * ny * nz;
-    k_dense_lines<<<lin_grid(c, total), 256, 0, c->stream>>>(in, out, gg, M);
+    BK_CHECK(c, !fused, "internal: fused transform on the general path");
+    BK_TRY(gen_launch(c, d, strided, pc.ttype[d] == 1 ? 2 : mode, in, out, g));
   }
   c->stats.kernel_launches++;
-  BK_CUDA(c, cudaGetLastError());
   return BK_OK;
 }
+
+static inline bool aligned16(const void* a, const void* b) { return ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0; }
 
 int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) {
   Precond& pc = c->pc;
@@ -431,114 +414,99 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
   BK_CHECK(c, in != out, "preconditioner: in-place application is not supported");
   const long long N = c->N;
   bool tail_done = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (c->timing) {  // per-application device time for bench.py's breakdown (event pairs are read back in bk_get_stats)
+    if (c->pc_pairs_used >= c->pc_pairs.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      c->pc_pairs.push_back({a, b});
+    }
+    ev0 = c->pc_pairs[c->pc_pairs_used].first;
+    ev1 = c->pc_pairs[c->pc_pairs_used].second;
+    c->pc_pairs_used++;
+    cudaEventRecord(ev0, c->stream);
+  }
+  const bool al = aligned16(in, out);
   if (pc.kind == BK_PC_SH_DCT) {
     const int nx = (int)c->dims[0], ny = (int)c->dims[1], nz = c->kind == BK_SH3D ? (int)c->dims[2] : 1;
     const int nd = c->kind == BK_SH3D ? 3 : 2;
     double* A = pc.work;
     double* B = pc.work2;
     const int last = nd - 1;
-    if (pc.pow2[last]) {
+    double scale = 1.0;
+    for (int d = 0; d < nd; ++d) scale /= 2.0 * (double)c->dims[d];
+    if (pc.fast[last] && al) {
       // x fwd, [y fwd,] (last dim: fwd + symbol + inverse in one kernel), [y inv,] x inv
-      SymbolArgs sy{pc.lam[last], pc.lam[0], nd == 3 ? pc.lam[1] : nullptr, pc.a0, nullptr, nullptr, 0};
+      bkf::Symbol sy{pc.lam[0], nd == 3 ? pc.lam[1] : nullptr, pc.a0, scale, nullptr, nullptr, 0};
       if (n > N && n - N <= 32) {  // border entries ride along with the fused kernel
         sy.tail_src = in + N;
         sy.tail_dst = out + N;
         sy.tail_n = (int)(n - N);
         tail_done = true;
       }
-      BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
+      BK_TRY(transform_pass(c, 0, 0, in, A, nx, ny, nz, al));
       if (nd == 3) {
-        BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
-        BK_TRY(transform_pass(c, 2, +1, B, A, nx, ny, nz, &sy));
-        BK_TRY(transform_pass(c, 1, -1, A, B, nx, ny, nz));
-        BK_TRY(transform_pass(c, 0, -1, B, out, nx, ny, nz));
+        BK_TRY(transform_pass(c, 1, 0, A, B, nx, ny, nz, true));
+        BK_TRY(transform_pass(c, 2, 0, B, A, nx, ny, nz, true, &sy));
+        BK_TRY(transform_pass(c, 1, 1, A, B, nx, ny, nz, true));
+        BK_TRY(transform_pass(c, 0, 1, B, out, nx, ny, nz, al));
       } else {
-        BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz, &sy));
-        BK_TRY(transform_pass(c, 0, -1, B, out, nx, ny, nz));
+        BK_TRY(transform_pass(c, 1, 0, A, B, nx, ny, nz, true, &sy));
+        BK_TRY(transform_pass(c, 0, 1, B, out, nx, ny, nz, al));
       }
     } else {
-      BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, nz));
-      BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, nz));
+      BK_TRY(transform_pass(c, 0, 0, in, A, nx, ny, nz, al));
+      BK_TRY(transform_pass(c, 1, 0, A, B, nx, ny, nz, true));
       double* cur = B;
       double* oth = A;
       if (nd == 3) {
-        BK_TRY(transform_pass(c, 2, +1, B, A, nx, ny, nz));
+        BK_TRY(transform_pass(c, 2, 0, B, A, nx, ny, nz, true));
         cur = A;
         oth = B;
       }
       k_sh_symbol_div<<<lin_grid(c, N), 256, 0, c->stream>>>(cur, nx, ny, nz, pc.lam[0], pc.lam[1],
-                                                            nd == 3 ? pc.lam[2] : nullptr, pc.a0);
+                                                            nd == 3 ? pc.lam[2] : nullptr, pc.a0, scale);
       c->stats.kernel_launches++;
       BK_CUDA(c, cudaGetLastError());
       if (nd == 3) {
-        BK_TRY(transform_pass(c, 2, -1, cur, oth, nx, ny, nz));
+        BK_TRY(transform_pass(c, 2, 1, cur, oth, nx, ny, nz, true));
         std::swap(cur, oth);
       }
-      BK_TRY(transform_pass(c, 1, -1, cur, oth, nx, ny, nz));
-      BK_TRY(transform_pass(c, 0, -1, oth, out, nx, ny, nz));
+      BK_TRY(transform_pass(c, 1, 1, cur, oth, nx, ny, nz, true));
+      BK_TRY(transform_pass(c, 0, 1, oth, out, nx, ny, nz, al));
     }
   } else if (pc.kind == BK_PC_CGL_DST) {
     const int nx = (int)c->dims[0], ny = (int)c->dims[1];
     const long long nblk = (c->kind == BK_POTRAP_CGL2D) ? 2 * c->dims[2] : 2;  // components x slices
     double* A = pc.work;
     double* B = pc.work2;
-    if (pc.blas && getenv("BK_CGL_DST_GEMM")) {
-      // Opt-in (not yet run on a GPU): the four dense DST-I passes as GEMMs, as BK_PC_POTRAP_CIRC does.  k_dense_lines costs
-      // 2.4 ms per apply at 512^2 x 2 fields (Floquet: 21 s for 48 monodromy applications); the GEMMs should be ~0.15 ms.
-      cublasHandle_t hnd = (cublasHandle_t)pc.blas;
-      const double one = 1.0, zero = 0.0;
-      const long long nn = (long long)nx * ny;
-      const int nf = (int)nblk;
-      const double* Sx = pc.dense[0];
-      const double* Sy = pc.dense[1];
-      BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, in, nx, &zero, A, nx) ==
-                      CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
-      BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, A, nx, nn, Sy, ny, 0, &zero, B, nx, nn,
-                                            nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
-      k_helmholtz_symbol_div<<<lin_grid(c, nn * nblk), 256, 0, c->stream>>>(B, nx, ny, nblk, pc.lam[0], pc.lam[1], pc.a0, pc.a1);
-      BK_CUDA(c, cudaGetLastError());
-      BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, B, nx, nn, Sy, ny, 0, &zero, A, nx, nn,
-                                            nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
-      BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, A, nx, &zero, out, nx) ==
-                      CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
-      c->stats.kernel_launches += 5;
-      if (c->kind == BK_POTRAP_CGL2D) BK_CUDA(c, cudaMemcpyAsync(out + N - 1, in + N - 1, 8, cudaMemcpyDeviceToDevice, c->stream));
-    } else {
-    BK_TRY(transform_pass(c, 0, +1, in, A, nx, ny, (int)nblk));
-    BK_TRY(transform_pass(c, 1, +1, A, B, nx, ny, (int)nblk));
+    BK_TRY(transform_pass(c, 0, 0, in, A, nx, ny, (int)nblk, al));
+    BK_TRY(transform_pass(c, 1, 0, A, B, nx, ny, (int)nblk, true));
     k_helmholtz_symbol_div<<<lin_grid(c, (long long)nx * ny * nblk), 256, 0, c->stream>>>(B, nx, ny, nblk, pc.lam[0], pc.lam[1],
                                                                                          pc.a0, pc.a1);
     c->stats.kernel_launches++;
     BK_CUDA(c, cudaGetLastError());
-    BK_TRY(transform_pass(c, 1, -1, B, A, nx, ny, (int)nblk));
-    BK_TRY(transform_pass(c, 0, -1, A, out, nx, ny, (int)nblk));
+    BK_TRY(transform_pass(c, 1, 1, B, A, nx, ny, (int)nblk, true));
+    BK_TRY(transform_pass(c, 0, 1, A, out, nx, ny, (int)nblk, al));
     if (c->kind == BK_POTRAP_CGL2D) BK_CUDA(c, cudaMemcpyAsync(out + N - 1, in + N - 1, 8, cudaMemcpyDeviceToDevice, c->stream));
-    }
   } else if (pc.kind == BK_PC_POTRAP_CIRC) {
     const int nx = (int)c->dims[0], ny = (int)c->dims[1], M = (int)c->dims[2];
     const long long nn = (long long)nx * ny, Ns = 2 * nn;
     const int nf = 2 * M;
-    cublasHandle_t hnd = (cublasHandle_t)pc.blas;
-    const double one = 1.0, zero = 0.0;
     double* A = pc.work;
     double* Bf = pc.work2;
-    const double* Sx = pc.dense[0];
-    const double* Sy = pc.dense[1];
-    // DST-I in space as dense GEMMs (the DST-I of 512 points needs a 1026-point FFT; fp64 GEMM is ~2 ms at 512^2 x 60):
-    // column-major view of a field = nx x ny;  A = Sx * in (all fields at once),  B_f = A_f * Sy (batched)
-    BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, in, nx, &zero, A, nx) ==
-                    CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
-    BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, A, nx, nn, Sy, ny, 0, &zero, Bf, nx, nn,
-                                          nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
+    // DST-I in space over all 2M slice components (mixed-radix FFT of the odd extension, bk_fft_gen.cuh), the circulant
+    // solve in time per spatial mode, DST-I back
+    BK_TRY(transform_pass(c, 0, 0, in, A, nx, ny, nf, al));
+    BK_TRY(transform_pass(c, 1, 0, A, Bf, nx, ny, nf, true));
     k_potrap_time<<<(unsigned)((nn + 127) / 128), 128, 0, c->stream>>>(Bf, nn, nx, M - 1, pc.lam[0], pc.lam[1], pc.po_T / M,
                                                                     pc.po_r, pc.po_nu, pc.tdft);
     BK_CUDA(c, cudaGetLastError());
-    BK_CHECK(c, cublasDgemmStridedBatched(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny, ny, &one, Bf, nx, nn, Sy, ny, 0, &zero, A, nx, nn,
-                                          nf) == CUBLAS_STATUS_SUCCESS, "cublasDgemmStridedBatched failed");
-    BK_CHECK(c, cublasDgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, nx, ny * nf, nx, &one, Sx, nx, A, nx, &zero, out, nx) ==
-                    CUBLAS_STATUS_SUCCESS, "cublasDgemm failed");
+    BK_TRY(transform_pass(c, 1, 1, Bf, A, nx, ny, nf, true));
+    BK_TRY(transform_pass(c, 0, 1, A, out, nx, ny, nf, al));
     k_potrap_close<<<(unsigned)((Ns + 255) / 256), 256, 0, c->stream>>>(in, out, Ns, M);
-    c->stats.kernel_launches += 6;
+    c->stats.kernel_launches += 2;
     BK_CUDA(c, cudaGetLastError());
   } else if (pc.kind == BK_PC_CHAN_TRIDIAG) {
     k_thomas<<<1, 32, 0, c->stream>>>(pc.tri, in, out, (int)N);
@@ -547,6 +515,7 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
   }
   if (n > N && !tail_done)
     BK_CUDA(c, cudaMemcpyAsync(out + N, in + N, 8 * (size_t)(n - N), cudaMemcpyDeviceToDevice, c->stream));
+  if (ev1) cudaEventRecord(ev1, c->stream);
   return BK_OK;
 }
 
