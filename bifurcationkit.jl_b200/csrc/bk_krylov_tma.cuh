@@ -89,7 +89,10 @@ __device__ __forceinline__ void ring_init(Ring* rg, int NS) {
 
 // Streams V_0..V_{j-1} restricted to the tile through the ring.  MODE 0: sred[i*8 + warp] = warp partial of
 // <V_i, val>; MODE 1: val -= g_i V_i.  Called by all BK2_THREADS threads after a __syncthreads().
-template <int E, int MODE>
+// REV: the basis is traversed from V_{j-1} down to V_0.  Pass 1 (dots) runs forward and pass 2 (update) backward, so each
+// pass starts with the vectors the previous pass touched last, which are still in the 126 MB L2 (with both passes forward
+// the LRU order evicts exactly what is needed next: 11 % hit rate in profiles/r01c_ncu_k2_fused.csv).
+template <int E, int MODE, bool REV = false>
 __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __restrict__ V, long long ld, int j, double* ring,
                                              int NS, Ring* rg, double (&val)[E], double* sred,
                                              const double* __restrict__ gcoef) {
@@ -105,7 +108,7 @@ __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __re
         const int s = i % NS, round = i / NS;
         if (round > 0) mbar_wait(&rg->empty[s], (unsigned)((round - 1) & 1));
         mbar_arrive_expect_tx(&rg->full[s], total);
-        const double* src = V + (long long)i * ld + tl.base;
+        const double* src = V + (long long)(REV ? j - 1 - i : i) * ld + tl.base;
         double* dst = ring + (size_t)s * (E * BK2_ROW);
         if (contiguous) {
           bulk_g2s(dst, src, total, &rg->full[s]);
@@ -160,7 +163,7 @@ __device__ __forceinline__ void stream_basis(const Tile2& tl, const double* __re
         const int s = i % NS;
         mbar_wait(&rg->full[s], (unsigned)((i / NS) & 1));
         const double* st = ring + (size_t)s * (E * BK2_ROW) + t;
-        const double g = __ldg(gcoef + i);
+        const double g = __ldg(gcoef + (REV ? j - 1 - i : i));
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
@@ -237,20 +240,36 @@ struct Sh2Scratch {
 
 // BORDERED (MatrixFreeBLSmap, src/LinearBorderSolver.jl:312-325): val += x_p * a + shift * v, and *bsum accumulates this
 // thread's share of <b, x_u>.
+// The input tile (E + 4 rows, clamped at the grid edge) is staged by the TMA engine: one cp.async.bulk per row for the
+// central 256 columns (16-byte aligned: x0 is a multiple of 256 and nx is even), issued by the producer lane and counted
+// on `tbar`; the 2 + 2 halo columns of every row are clamped scalar loads by 4 (E + 4) threads.  The stencil is linear in
+// v, so the deferred normalisation in_scale is applied to the results instead of the staged tile.
 template <int E, bool BORDERED>
 __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __restrict__ in, double in_scale, int x0, int y0,
-                                              double* scratch, double (&val)[E], double xp, double* bsum) {
+                                              double* scratch, unsigned long long* tbar, double (&val)[E], double xp,
+                                              double* bsum) {
   using S = Sh2Scratch<E>;
   double* vs = scratch;
   double* qs = scratch + S::V_ELEMS;
   const int nx = op.nx, ny = op.ny;
-  for (int q = threadIdx.x; q < S::V_ELEMS; q += blockDim.x) {
-    int i = q % S::VX, jj = q / S::VX;
+  const int len = min(BK2_ROW, nx - x0);
+  if (threadIdx.x == BK2_CONS) {
+    mbar_arrive_expect_tx(tbar, (unsigned)(len * 8) * (unsigned)S::VY);
+#pragma unroll 1
+    for (int jj = 0; jj < S::VY; ++jj) {
+      int gy = y0 - 2 + jj;
+      gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
+      bulk_g2s(vs + jj * S::VX + 2, in + x0 + (long long)gy * nx, (unsigned)(len * 8), tbar);
+    }
+  } else if (threadIdx.x < 4 * S::VY) {
+    const int jj = threadIdx.x >> 2, h = threadIdx.x & 3;
+    const int i = h < 2 ? h : len + h;  // 0, 1, len + 2, len + 3
     int gx = x0 - 2 + i, gy = y0 - 2 + jj;
     gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
     gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
-    vs[q] = in_scale * __ldg(in + gx + (long long)gy * nx);
+    vs[jj * S::VX + i] = __ldg(in + gx + (long long)gy * nx);
   }
+  mbar_wait(tbar, 0);
   __syncthreads();
   for (int q = threadIdx.x; q < S::Q_ELEMS; q += blockDim.x) {
     int i = q % S::QX, jj = q / S::QX;
@@ -271,8 +290,8 @@ __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __
     if (t < BK2_ROW && gx < nx && gy < ny) {
       const double* p = qs + (t + 1) + (e + 1) * S::QX;
       const double c0 = p[0];
-      const double l1v = c0 + op.cx * (p[-1] - 2.0 * c0 + p[1]) + op.cy * (p[-S::QX] - 2.0 * c0 + p[S::QX]);
-      const double v = vs[(t + 2) + (e + 2) * S::VX];
+      const double l1v = in_scale * (c0 + op.cx * (p[-1] - 2.0 * c0 + p[1]) + op.cy * (p[-S::QX] - 2.0 * c0 + p[S::QX]));
+      const double v = in_scale * vs[(t + 2) + (e + 2) * S::VX];
       const double uu = __ldg(op.u + gx + (long long)gy * nx);
       const double coef = l + uu * (2.0 * nu - 3.0 * uu);
       r = op.a0 * v + op.a1 * (coef * v - l1v);
@@ -294,40 +313,45 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
                                                                   double* __restrict__ partials, unsigned int* counter,
                                                                   double* __restrict__ hcol, double* __restrict__ gcoef,
                                                                   int NS, int sred_off) {
-#ifndef BK2_LATE_WAIT
-  bk_pdl_sync();
-#endif
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
+  __shared__ __align__(8) unsigned long long tbar;
   __shared__ int s_flag;
   double* ring = smem2;
   double* sred = smem2 + sred_off;
+  // barrier set-up and tile arithmetic overlap the tail of the previous kernel (PDL): nothing it wrote is read before the wait
+  if (threadIdx.x == 0) mbar_init(&tbar, 1);
   ring_init(&rg, NS);
   const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
   const int x0 = (blockIdx.x % tiles_x) * BK2_ROW, y0 = (blockIdx.x / tiles_x) * E;
   double val[E];
-#ifdef BK2_LATE_WAIT
-  // experiment (build with EXTRA=-DBK2_LATE_WAIT, not yet measured): barrier set-up and tile arithmetic overlap the tail of
-  // the previous kernel; nothing written by it has been read yet (the L2 prefetch below is only a hint)
-  bk_pdl_sync();
-#endif
-  const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
   Tile2 tl;
   tl.base = x0 + (long long)y0 * op.nx;
   tl.rs = op.nx;
   tl.rows = min(E, op.ny - y0);
   tl.len = min(BK2_ROW, op.nx - x0);
   tl.last_len = tl.len;
+  __syncthreads();  // barriers initialised before the producer lane arms them
+  bk_pdl_sync();
+  const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
   if (threadIdx.x == BK2_CONS) {
-    // the ring cannot start before the stencil scratch is dead: pull the first basis tiles into L2 meanwhile
+    // pull what the stencil epilogue and the first ring rounds will read into L2 while the tile is in flight
     const unsigned row_b = (unsigned)(((tl.len + 1) & ~1) * 8);
+    for (int r = 0; r < tl.rows; ++r) {
+      const long long o = tl.base + (long long)r * tl.rs;
+      bulk_prefetch_l2(op.u + o, row_b);
+      if (BORDERED) {
+        bulk_prefetch_l2(op.ba + o, row_b);
+        bulk_prefetch_l2(op.bb + o, row_b);
+      }
+    }
     const int npf = j < 2 * NS ? j : 2 * NS;
     for (int i = 0; i < npf; ++i)
       for (int r = 0; r < tl.rows; ++r) bulk_prefetch_l2(V + (long long)i * ld + tl.base + (long long)r * tl.rs, row_b);
   }
   const double xp = BORDERED ? s * __ldg(in + op.N) : 0.0;
   double bsum = 0.0;
-  sh2_tile_eval<E, BORDERED>(op, in, s, x0, y0, smem2, val, xp, &bsum);
+  sh2_tile_eval<E, BORDERED>(op, in, s, x0, y0, smem2, &tbar, val, xp, &bsum);
   if (threadIdx.x < tl.len) {
 #pragma unroll
     for (int e = 0; e < E; ++e)
@@ -376,7 +400,6 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_dots(const double* _
                                                                  double* __restrict__ partials, unsigned int* counter,
                                                                  double* __restrict__ hcol, double* __restrict__ gcoef, int NS,
                                                                  int sred_off) {
-  bk_pdl_sync();
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
   __shared__ int s_flag;
@@ -385,6 +408,7 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_dots(const double* _
   ring_init(&rg, NS);
   const Tile2 tl = linear_tile(n, E);
   double val[E];
+  bk_pdl_sync();  // after the barrier set-up: it overlaps the tail of the previous kernel
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
@@ -403,7 +427,6 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_update(const double*
                                                                    double* __restrict__ partials, unsigned int* counter,
                                                                    double* __restrict__ h_out, double* __restrict__ scale_out,
                                                                    int NS) {
-  bk_pdl_sync();
   extern __shared__ __align__(128) double smem2[];
   __shared__ Ring rg;
   __shared__ double s_w[9];
@@ -413,13 +436,14 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_update(const double*
   const Tile2 tl = linear_tile(n, E);
   double val[E];
   const int t = threadIdx.x;
+  bk_pdl_sync();  // after the barrier set-up: it overlaps the tail of the previous kernel
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int lim = (e == tl.rows - 1) ? tl.last_len : tl.len;
     val[e] = (t < BK2_ROW && e < tl.rows && t < lim) ? w[tl.base + e * BK2_ROW + t] : 0.0;
   }
   __syncthreads();
-  stream_basis<E, 1>(tl, V, ld, j, ring, NS, &rg, val, nullptr, gcoef);
+  stream_basis<E, 1, true>(tl, V, ld, j, ring, NS, &rg, val, nullptr, gcoef);
   double acc = 0.0;
   if (t < BK2_ROW) {
 #pragma unroll
