@@ -36,8 +36,12 @@ struct Cfg {
   static constexpr int NP = F + (RB ? 1 : 0);
   static constexpr int PP = (T >= 32) ? 2 : 64 / T;                // line pairs per CTA
   static constexpr int THREADS = T * PP;
-  static constexpr int PB = (LOGE == 5 && LOGN >= 10) ? 5 : 4;
-  __host__ __device__ static constexpr int pad(int i) { return i + (i >> 2) + (i >> PB); }
+  // second padding shift, chosen per (E, n) with the bank model (tools/fftcheck/model.py); 0 = none
+  static constexpr int PB = LOGE == 5 ? (LOGN >= 10 ? 5 : 4) : LOGE == 4 ? 4 : LOGE == 3 ? ((LOGN == 9 || LOGN == 10) ? 3 : 0) : 0;
+  __host__ __device__ static constexpr int pad(int i) { return i + (i >> 2) + (PB ? (i >> PB) : 0); }
+  // resident threads per SM the register budget is sized for (launch bounds): few fat threads (E = 32: 255 registers) ... many thin ones
+  static constexpr int TPSM = LOGE == 5 ? 256 : LOGE == 4 ? 512 : LOGE == 3 ? 768 : 1024;
+  static constexpr int MINB = TPSM / THREADS > 0 ? TPSM / THREADS : 1;
   static constexpr int SLOTS = pad(N - 1) + 1;                     // padded complex slots per pair
   static constexpr size_t SMEM = sizeof(double2) * (size_t)SLOTS * PP;
   __host__ __device__ static constexpr int logr(int p) { return p < F ? LOGE : RB; }
@@ -50,7 +54,7 @@ struct Cfg {
   }
   static constexpr int TW_TOTAL = tw_off(NP);
   static_assert(LOGN >= LOGE + 1 && LOGN <= 11, "line length out of range");
-  static_assert(T <= 64, "at most 64 threads per line pair");
+  static_assert(THREADS <= 1024, "CTA too large");
 };
 
 // position <-> frequency (digit reversal in units of LOGE bits, last digit RB bits)
@@ -333,7 +337,7 @@ __device__ __forceinline__ void strided_store(const double2 (&a)[C::E], double* 
   }
 }
 
-#define BKF_BOUNDS(C) __launch_bounds__(C::THREADS, (C::LOGE == 5 ? 256 : 512) / C::THREADS)
+#define BKF_BOUNDS(C) __launch_bounds__(C::THREADS, C::MINB)
 
 // MODE 0: forward (out = 2 C, natural k along the line), 1: inverse (out = n x from C), 2: forward, divide by the symbol, inverse
 template <class C, int MODE>

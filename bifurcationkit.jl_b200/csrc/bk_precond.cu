@@ -25,7 +25,7 @@
 #include "bk_fft_gen.cuh"
 
 #ifndef BK_FFT_LOGE
-#define BK_FFT_LOGE 5   // complex values per thread of the fast kernels: 2^5 = 32 (n = 1024 = 32 x 32: one exchange per FFT)
+#define BK_FFT_LOGE 3   // default log2 of the complex values per thread of the fast kernels (measured on B200)
 #endif
 
 // divide by the symbol
@@ -145,23 +145,40 @@ static int upload(bk_ctx* c, void** dst, const void* src, size_t bytes) {
   return BK_OK;
 }
 
-// ---- fast path: one instantiation per line length -------------------------------------------------------------------------
+// ---- fast path: one instantiation per (values per thread, line length) -----------------------------------------------------
+// BK_FFT_LOGE (environment, read at bk_precond_setup): log2 of the complex values a thread owns, 2..5.  Default: see fast_loge().
+static int fast_loge() {
+  static int e = -1;
+  if (e < 0) {
+    const char* a = getenv("BK_FFT_LOGE");
+    e = a ? atoi(a) : BK_FFT_LOGE;
+    if (e < 2 || e > 5) e = BK_FFT_LOGE;
+  }
+  return e;
+}
 static int fast_logn(long long n) {
   static int off = -1;
   if (off < 0) off = getenv("BK_FFT_NO_FAST") ? 1 : 0;  // diagnostics: force the general kernel everywhere
   if (off) return 0;
-  for (int l = BK_FFT_LOGE + 1; l <= 11; ++l)
-    if (n == (1LL << l)) return l;
+  for (int l = fast_loge() + 1; l <= 11; ++l)
+    if (l >= 6 && n == (1LL << l)) return l;
   return 0;
 }
-#define BKF_DISPATCH(LOGN, ...)                                                        \
+#define BKF_DISPATCH_N(LE, LOGN, ...)                                                   \
   switch (LOGN) {                                                                      \
-    case 6: { using FC = bkf::Cfg<6, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
-    case 7: { using FC = bkf::Cfg<7, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
-    case 8: { using FC = bkf::Cfg<8, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
-    case 9: { using FC = bkf::Cfg<9, BK_FFT_LOGE>; __VA_ARGS__; } break;               \
-    case 10: { using FC = bkf::Cfg<10, BK_FFT_LOGE>; __VA_ARGS__; } break;             \
-    default: { using FC = bkf::Cfg<11, BK_FFT_LOGE>; __VA_ARGS__; } break;             \
+    case 6: { using FC = bkf::Cfg<6, LE>; __VA_ARGS__; } break;                        \
+    case 7: { using FC = bkf::Cfg<7, LE>; __VA_ARGS__; } break;                        \
+    case 8: { using FC = bkf::Cfg<8, LE>; __VA_ARGS__; } break;                        \
+    case 9: { using FC = bkf::Cfg<9, LE>; __VA_ARGS__; } break;                        \
+    case 10: { using FC = bkf::Cfg<10, LE>; __VA_ARGS__; } break;                      \
+    default: { using FC = bkf::Cfg<11, LE>; __VA_ARGS__; } break;                      \
+  }
+#define BKF_DISPATCH(LOGN, ...)                                                        \
+  switch (fast_loge()) {                                                               \
+    case 2: BKF_DISPATCH_N(2, LOGN, __VA_ARGS__) break;                                \
+    case 3: BKF_DISPATCH_N(3, LOGN, __VA_ARGS__) break;                                \
+    case 4: BKF_DISPATCH_N(4, LOGN, __VA_ARGS__) break;                                \
+    default: BKF_DISPATCH_N(5, LOGN, __VA_ARGS__) break;                               \
   }
 
 template <class FC>
