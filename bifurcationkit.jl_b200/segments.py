@@ -103,3 +103,144 @@ def merge_branch(gathered):
         if len(seg):
             out.append(seg)
     return np.concatenate(out) if out else np.zeros((0, len(ROW)))
+
+
+# ======================================================================================================================
+# Round 2: one branch WINDOW of fixed arclength, the same for every number of GPUs (strong scaling), partitioned by
+# predicted cost from a cheap scout that is itself part of the timed job.
+#
+#   window   : the curve from the start point over the PALC arclength S (theta-norm chord length, src/continuation/Palc.jl:1-41)
+#   scout    : the same PALC iteration with loose tolerances and larger steps (a seed generator, not a result): every rank
+#              runs it itself, deterministically -- the library's reductions have a fixed order -- so no state ever crosses
+#              NVLink; it records the points z_j, their arclength positions sigma_j and a cost proxy
+#   partition: contiguous chunks of scout intervals with equal predicted cost, one per rank
+#   chunk    : full-accuracy PALC from the seed pair (z_i, z_{i+1}) through the reference's two-point start
+#              (iterate_from_two_points, src/Continuation.jl:408-456) until the curve passes the next rank's seed
+#   collective: all_gather of the rows (lambda, ||u||, itnewton, itlinear) only, as before
+# ======================================================================================================================
+def _chord(V, theta, z_u, z_p, w_u, w_p):
+    """theta-norm of (z - w): sqrt(theta/N ||z_u - w_u||^2 + (1 - theta) (z_p - w_p)^2), two reductions"""
+    n = len(z_u)
+    d2 = V.diffdot(z_u, w_u, z_u) - V.diffdot(z_u, w_u, w_u)
+    return float(np.sqrt(max(0.0, theta * d2 / n + (1.0 - theta) * (z_p - w_p) ** 2)))
+
+
+class ArcTracker:
+    """Continuation callback: accumulates the chord arclength of the accepted steps and stops at `s_stop`."""
+
+    def __init__(self, V, theta, s0=0.0, s_stop=np.inf, on_point=None):
+        self.V, self.theta, self.s, self.s_stop, self.on_point = V, theta, float(s0), s_stop, on_point
+        self.sigma = []
+
+    def __call__(self, st):
+        if st.step > 0:
+            self.s += _chord(self.V, self.theta, st.z_u, st.z_p, st.zold_u, st.zold_p)
+        self.sigma.append(self.s)
+        keep = True
+        if self.on_point is not None:
+            r = self.on_point(st, self.s)
+            keep = True if r is None else bool(r)
+        return keep and self.s < self.s_stop
+
+
+class Scout:
+    """Seed points of the window: points[j] = (u, p), sigma[j] = arclength position, cost[j] = predicted cost of the
+    full-accuracy run between point j-1 and j."""
+
+    def __init__(self):
+        self.points, self.sigma, self.cost, self.rows = [], [], [], []
+
+
+def run_scout(P, prob, alg, cp_scout, normC, s_total, copy, margin=0.0):
+    """Loose continuation from the start point over arclength s_total (+ margin); returns a Scout."""
+    V = P.V
+    sc = Scout()
+
+    def on_point(st, s):
+        sc.points.append((copy(st.z_u), st.z_p))
+        return True
+
+    trk = ArcTracker(V, alg.theta, 0.0, s_total + margin, on_point)
+    rows, st = P.continuation(prob, alg, cp_scout, normC=normC, callback=trk)
+    sc.sigma = list(trk.sigma)
+    sc.rows = rows[: len(sc.sigma)]
+    # cost proxy of the interval ending at point j: its arclength (= number of full-accuracy steps at dsmax) weighted by
+    # the Krylov work the scout needed there (+ a constant for the per-step overhead)
+    sc.cost = [0.0] + [(sc.sigma[j] - sc.sigma[j - 1]) * (20.0 + sc.rows[j]["itlinear"] / max(1, sc.rows[j]["itnewton"]))
+                       for j in range(1, len(sc.sigma))]
+    return sc
+
+
+def partition_by_cost(cost, world, min_points=2):
+    """Boundaries b[0] = 0 < b[1] < ... < b[world] = J over the scout intervals 1..J such that every chunk
+    (b[r], b[r+1]] carries about the same cost and at least one interval.  Pure function (unit-tested on CPU)."""
+    J = len(cost) - 1
+    world = max(1, min(world, J))
+    c = np.cumsum(np.asarray(cost, dtype=float))
+    tot = c[-1] if c[-1] > 0 else 1.0
+    b = [0]
+    for r in range(1, world):
+        j = int(np.searchsorted(c, tot * r / world))
+        j = min(max(j, b[-1] + 1), J - (world - r))
+        b.append(j)
+    b.append(J)
+    return b
+
+
+def run_chunk(P, make_prob, alg, cp, normC, sc, i0, i1, s_total, rank, last):
+    """Full-accuracy PALC over the scout intervals (i0, i1]: two-point start from (z_i0, z_i0+1) -- rank 0 starts from the true
+    start point the usual way -- until the curve passes seed i1 (or, for the last rank, the end of the window).
+    Returns (rows, state); rows[0] (the seed itself) is dropped for rank > 0."""
+    V, theta = P.V, alg.theta
+    u0, p0 = sc.points[i0]
+    prob = make_prob(u0, p0)
+    end_u, end_p = sc.points[i1]
+    # tangent of the scout polyline at the end seed (towards increasing arclength)
+    nb_u, nb_p = sc.points[i1 - 1]
+    s_end, s_start = sc.sigma[i1], sc.sigma[i0]
+    near = s_end - 2.5 * (s_end - sc.sigma[i1 - 1])
+
+    def passed(st, s):
+        if last:
+            return s < s_total
+        if s < near:
+            return True
+        # projection of (z - z_end) on the end tangent (z_end - z_prev) in the theta inner product
+        n = len(st.z_u)
+        du = V.diffdot(st.z_u, end_u, end_u) - V.diffdot(st.z_u, end_u, nb_u)
+        proj = theta * du / n + (1.0 - theta) * (st.z_p - end_p) * (end_p - nb_p)
+        return proj < 0.0
+
+    trk = ArcTracker(V, theta, s_start, np.inf, passed)
+    if rank == 0 and i0 == 0:
+        rows, st = P.continuation(prob, alg, cp, normC=normC, callback=trk)
+        return rows, st, trk
+    u1, p1 = sc.points[i0 + 1]
+    rows, st = P.continuation(prob, alg, cp, normC=normC, u1=u1, p1=p1, callback=trk)
+    return rows[1:], st, trk
+
+
+def merge_chunks(gathered):
+    """Rank-ordered concatenation of the gathered (world, nrows, 4) rows, padding dropped."""
+    out = [seg[~np.isnan(seg[:, 0])] for seg in gathered]
+    out = [s for s in out if len(s)]
+    return np.concatenate(out) if out else np.zeros((0, len(ROW)))
+
+
+def curve_distance(branch, ref):
+    """max over the points of `branch` of the distance to the polyline `ref` in the (lambda, x) plane, both columns scaled
+    by the extent of `ref` -- the arclength-interpolation parity check of SURVEY 8e (segment boundaries and adaptive ds
+    change WHICH points are computed, not the curve)."""
+    a = np.asarray(branch)[:, :2].astype(float)
+    b = np.asarray(ref)[:, :2].astype(float)
+    sc = np.maximum(b.max(0) - b.min(0), 1e-300)
+    a, b = a / sc, b / sc
+    worst = 0.0
+    for p in a:
+        d = np.inf
+        for q0, q1 in zip(b[:-1], b[1:]):
+            v = q1 - q0
+            t = 0.0 if not np.any(v) else min(1.0, max(0.0, float(np.dot(p - q0, v) / np.dot(v, v))))
+            d = min(d, float(np.linalg.norm(p - (q0 + t * v))))
+        worst = max(worst, d)
+    return worst

@@ -119,6 +119,72 @@ def test_two_point_start_continues_the_same_curve():
             assert abs(np.interp(r["x"], fx, fp) - r["param"]) < 2e-2
 
 
+def _chan_window_setup(bk, n=31):
+    P = bk.palc
+    beta = 0.01
+    F = lambda x, a: problems.chan_F(x, a, beta)
+
+    def Jd(x, a):
+        E = np.eye(n)
+        return np.column_stack([problems.chan_dF(x, E[:, k], a, beta) for k in range(n)])
+
+    ls = krylov.DefaultLS()
+    mk = lambda tol, dsmax, ds: P.ContinuationPar(dsmin=0.005, dsmax=dsmax, ds=ds, p_max=4.2, p_min=-1.0, max_steps=400,
+                                                  newton_options=P.NewtonPar(tol=tol, max_iterations=10, linsolver=ls))
+    alg = P.PALC(bls=BlsAdapter(obls.MatrixBLS()))
+    make_prob = lambda u, p: NumpyProblem(F, Jd, u, p)
+    return P, F, make_prob, alg, mk
+
+
+def _window_job(bk, rank, world, s_total=3.0):
+    """What one rank of bench.py --gpus N does: replicated cheap scout over the window, partition by predicted cost,
+    full-accuracy chunk through the two-point start."""
+    P, F, make_prob, alg, mk = _chan_window_setup(bk)
+    sc = bk.segments.run_scout(P, make_prob(problems.chan_sol0(31), 3.3), alg, mk(1e-4, 0.15, 0.05), P.norm2, s_total,
+                               lambda v: v.copy(), margin=0.3)
+    b = bk.segments.partition_by_cost(sc.cost, world)
+    rows, st, trk = bk.segments.run_chunk(P, make_prob, alg, mk(1e-10, 0.05, 0.05), P.norm2, sc, b[rank], b[rank + 1], s_total,
+                                          rank, rank == len(b) - 2)
+    return sc, b, rows, F
+
+
+def test_window_partition_traces_the_single_gpu_curve():
+    """SURVEY 8e parity: the union of the chunks (started from loose scout seeds) lies on the curve the single run
+    computes over the same arclength window -- compared by distance to the polyline, not row by row."""
+    bk = g.load_package()
+    P, F, make_prob, alg, mk = _chan_window_setup(bk)
+    s_total = 3.0
+    trk = bk.segments.ArcTracker(P.V, alg.theta, 0.0, s_total)
+    full, _ = P.continuation(make_prob(problems.chan_sol0(31), 3.3), alg, mk(1e-10, 0.05, 0.05), callback=trk)
+    ref = np.array([[r["param"], r["x"]] for r in full])
+    assert abs(trk.s - s_total) < 0.06 and len(full) > 40
+    # the same run a little further: the chunks measure arclength along their own polylines, so the window's end differs by O(ds)
+    longer, _ = P.continuation(make_prob(problems.chan_sol0(31), 3.3), alg, mk(1e-10, 0.05, 0.05),
+                               callback=bk.segments.ArcTracker(P.V, alg.theta, 0.0, s_total + 0.4))
+    ref_long = np.array([[r["param"], r["x"]] for r in longer])
+    for world in (1, 2, 4):
+        merged = []
+        for rank in range(world):
+            sc, b, rows, _ = _window_job(bk, rank, world, s_total)
+            assert len(sc.points) < 0.5 * len(full)                      # the scout is much coarser than the run itself
+            assert len(rows) >= 1
+            merged += [[r["param"], r["x"]] for r in rows]
+        merged = np.array(merged)
+        assert bk.segments.curve_distance(merged, ref_long) < 2e-3, world  # on the same curve (chords of the polyline: O(ds^2))
+        assert bk.segments.curve_distance(ref, merged) < 2e-2, world      # and covering the whole window
+        assert abs(len(merged) - len(full)) <= 4 * world                  # about the same number of steps: identical work
+
+
+def test_partition_by_cost_is_balanced_and_contiguous():
+    bk = g.load_package()
+    cost = [0.0] + [1.0] * 10 + [5.0] * 10 + [1.0] * 10
+    b = bk.segments.partition_by_cost(cost, 4)
+    assert b[0] == 0 and b[-1] == 30 and all(x < y for x, y in zip(b[:-1], b[1:]))
+    loads = [sum(cost[b[r] + 1: b[r + 1] + 1]) for r in range(4)]
+    assert max(loads) <= 1.5 * sum(cost) / 4
+    assert bk.segments.partition_by_cost([0.0, 1.0, 1.0], 8) == [0, 1, 2]   # more ranks than intervals
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
@@ -130,7 +196,11 @@ def _gloo_worker(rank, world, port, q):
     rows = [dict(param=-0.1 - 0.01 * (rank * 3 + i), x=1.0 + rank + 0.1 * i, itnewton=2, itlinear=40 + i) for i in range(4 - rank)]
     gathered = bk.segments.all_gather_rows(rows, 5, dist, torch, "cpu")
     merged = bk.segments.merge_branch(gathered)
-    q.put((rank, gathered.shape, merged.tolist()))
+    # the round-2 scheme end to end on 2 processes: replicated scout, cost partition, chunk, all_gather of the rows
+    sc, b, wrows, F = _window_job(bk, rank, world)
+    wg = bk.segments.all_gather_rows(wrows, 120, dist, torch, "cpu")
+    wmerged = bk.segments.merge_chunks(wg)
+    q.put((rank, gathered.shape, merged.tolist(), wmerged[:, :2].tolist(), b))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -149,6 +219,9 @@ def test_all_gather_rows_gloo_world2():
         assert p.exitcode == 0
     res.sort()
     assert res[0][1] == (2, 5, 4) and res[0][2] == res[1][2]      # every rank assembles the same branch
+    assert res[0][3] == res[1][3] and res[0][4] == res[1][4]       # same partition, same merged window on both ranks
+    w = np.array(res[0][3])
+    assert len(w) > 40 and np.all(np.diff(w[:, 1]) > 0)            # one monotone sweep along the Chan branch, no gap / overlap
     merged = np.array(res[0][2])
     assert merged.shape == (4 + 3 - 1, 4)                           # rank-1 segment starts at rank-0's last point (-0.13): dropped once
     assert np.all(np.diff(merged[:, 0]) < 0)
