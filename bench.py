@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- continuation steps/sec on 2-D Swift-Hohenberg (SH2d-fronts, fp64) + achieved HBM GB/s of the
+"""bench.py -- continuation steps/sec on 2-D Swift-Hohenberg (SH2d-fronts 1024^2, fp64) + achieved HBM GB/s of the
 fused JVP+Arnoldi kernel, per BASELINE.json.
 
-A "step" = one PALC continuation step (secant predictor + Newton-Krylov corrector: per Newton iteration
-2 residuals, 1 BorderingBLS solve = 2 GMRES solves with the DCT preconditioner on the right, fused
-JVP+Arnoldi kernels).  N=1 workload: SH2d-fronts 1024^2 (BASELINE.json configs[2] on one GPU; the metric is
-quoted on SH2d 1024^2).  For N>1 the branch is partitioned by continuation step: every rank advances its own
-segment of K steps from a seed produced by a deterministic scout run, state vectors are replicated, and the
-only collective is an all_gather of the (lambda, ||u||, itnewton, itlinear) rows (weak scaling).
+Workload (BASELINE.json configs[2]: "SH2d-fronts 1024^2, PALC branch of 200 steps sharded 8xB200"): the localized-front branch
+of examples/SH2d-fronts.jl from its start point over a fixed WINDOW of PALC arclength S = K * B * dsmax -- the same window for
+every number of GPUs (strong scaling).  A bench "step" = one BATCH of B = 10 continuation steps at dsmax (the unit after
+which the (lambda, ||u||) rows are exchanged, north_star); `value` = K * B / t in continuation steps per second, where a
+continuation step = secant predictor + Newton-Krylov corrector (per Newton iteration 2 residuals and one MatrixFreeBLS solve =
+one GMRES(100) with the DCT preconditioner on the right, fused JVP+Arnoldi kernels).  K = 20, B = 10 -> the 200-step branch.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 1024] [--impl reference]
+N = 1: plain continuation over the window.  N > 1: every rank runs a cheap, deterministic scout of the window itself
+(loose tolerances, larger steps; replicated state, nothing crosses NVLink), the window is cut into contiguous chunks of equal
+predicted cost, every rank advances its chunk at full accuracy from a scout seed pair (two-point start), and the rows are
+all_gathered.  The scout is INSIDE the timed region; the time of the job is the max over ranks.
 
---impl reference : times the CPU restatement of the reference path (oracle/, NumPy/SciPy -- Julia is absent
-from this image) on the host cores, on a bounded sample of the same workload.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 1024] [--batch 10] [--impl reference]
+
+--impl reference : times the CPU restatement of the reference path -- oracle/c, C++17/OpenMP on all host cores (CSR SpMV with the
+kron-assembled L1, MGS GMRES, DCT preconditioner); Julia is absent from this image, see DESIGN.md -- on a
+bounded sample of the same window.
 """
 import argparse
 import json
@@ -99,15 +105,17 @@ class ClockSampler:
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of k2_fused from the committed `ncu --set full` capture
-    (profiles/r01c_ncu_k2_fused.csv; j ~ 16 at capture time: algorithmic 8N(j+2) + 16N border = 168 MB)."""
-    p = os.path.join(ROOT, "profiles", "r01c_ncu_k2_fused.csv")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of k2_fused<8,1> from the committed `ncu --set full` capture of
+    the shipped kernel (profiles/r02_ncu_k2_fused.csv, falling back to the round-1 capture of k2_fused<7,1>)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_k2_fused.csv")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01c_ncu_k2_fused.csv")
     try:
         import csv
         rows = list(csv.reader(open(p)))
         h = rows[0]
         vals = [float(r[h.index("dram__bytes_read.sum")]) + float(r[h.index("dram__bytes_write.sum")]) for r in rows[2:]]
-        return {"bytes_per_launch": 1e6 * sum(vals) / len(vals), "source": "profiles/r01c_ncu_k2_fused.csv (k2_fused, one ncu --set full capture)"}
+        return {"bytes_per_launch": 1e6 * sum(vals) / len(vals), "source": os.path.relpath(p, ROOT) + " (k2_fused, one ncu --set full capture)"}
     except Exception:
         return None
 
@@ -249,20 +257,132 @@ def cpu_steps(n, u_start, p_start, nsteps, workers):
     return rows, (t1 - t0), 1
 
 
+class StepTimer:
+    """CUDA-event timing of continuation steps on the library's stream.  `wrap(cb)` returns a continuation callback that
+    closes the running step's event pair, flushes L2 (outside the pair) and opens the next pair, then calls `cb`."""
+
+    def __init__(self, ctx, torch, flush):
+        self.ctx, self.torch, self.flush = ctx, torch, flush
+        self.stream = torch.cuda.ExternalStream(ctx.lib.bk_stream(ctx.handle))
+        self.pairs, self.open = [], None
+
+    def _event(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.stream)
+        return e
+
+    def start(self):
+        """opens a pair now (used to time work that precedes a continuation loop's step 0: the start-up Newton solves of the scout)"""
+        if self.flush is not None:
+            with self.torch.cuda.stream(self.stream):
+                self.flush.zero_()
+        self.open = self._event()
+
+    def stop(self):
+        if self.open is not None:
+            self.pairs.append((self.open, self._event()))
+            self.open = None
+
+    def wrap(self, cb):
+        def f(st):
+            self.stop()
+            keep = cb(st) if cb is not None else True
+            self.start()
+            return keep
+        return f
+
+    def total_ms(self):
+        self.stop()
+        self.ctx.sync()
+        return float(sum(a.elapsed_time(b) for a, b in self.pairs))
+
+
+def make_algs(bk, ctx, ls, n):
+    """(fine alg, fine ContinuationPar factory, scout alg, scout ContinuationPar)"""
+    P = bk.palc
+    mkbls = lambda l: bk.MatrixFreeBLSB200(l) if BLS["kind"] == "matrixfree" else bk.BorderingBLSB200(l, check_precision=False)
+    alg = P.PALC(bls=mkbls(ls))
+    cp = lambda ds=None: P.ContinuationPar(max_steps=10**6, newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls),
+                                          **dict(CONT, ds=CONT["ds"] if ds is None else ds))
+    ls_s = bk.GMRESB200(N=n * n, Pr=True, **dict(GMRES, reltol=SCOUT["gmres_reltol"]))
+    cps = P.ContinuationPar(max_steps=10**6, newton_options=P.NewtonPar(tol=SCOUT["newton_tol"], max_iterations=SCOUT["newton_maxit"], linsolver=ls_s),
+                            **dict(CONT, dsmax=SCOUT["ds_factor"] * CONT["dsmax"], ds=SCOUT["ds_factor"] * CONT["ds"]))
+    return alg, cp, P.PALC(bls=mkbls(ls_s)), cps
+
+
+SCOUT = dict(ds_factor=4.0, newton_tol=1e-4, newton_maxit=8, gmres_reltol=1e-2)  # seed generator of the N > 1 partition (tools/scout_probe.py)
+
+
+def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timing=True, wrap=None):
+    """One rank's share of the window.  Returns (rows, ms, stats delta, info)."""
+    P, S = bk.palc, bk.segments
+    wrap = wrap or (lambda v: v)
+    alg, cpf, alg_s, cps = make_algs(bk, ctx, ls, n)
+    mkprob = lambda u, p: P.BifurcationProblemB200(ctx, u, [p] + list(PAR[1:]), lens=0)
+    tm = StepTimer(ctx, torch, flush)
+    ctx.sync()
+    ctx.set_timing(timing)
+    s0 = ctx.stats()
+    torch.cuda.profiler.start()
+    info = {"scout_ms": 0.0, "scout_points": 0, "chunk": None, "rejected": 0, "work_newton": 0, "work_linear": 0}
+    if world == 1:
+        trk = S.ArcTracker(P.V, alg.theta, 0.0, s_total)
+        rows, st = P.continuation(mkprob(u_start, PAR[0]), alg, cpf(), normC=P.norminf, callback=tm.wrap(trk))
+    else:
+        tm.start()  # the scout's two start-up Newton solves are part of the job
+        sc = S.run_scout(P, mkprob(u_start, PAR[0]), alg_s, cps, P.norminf, s_total, lambda v: wrap(v.copy() if hasattr(v, "copy") else v),
+                         margin=2.0 * SCOUT["ds_factor"] * CONT["dsmax"], wrap_callback=tm.wrap)
+        info["scout_ms"] = tm.total_ms()
+        tm.start()  # partition + the chunk's start-up belong to the job as well
+        info["scout_points"] = len(sc.points)
+        b = S.partition_by_cost(sc.cost, world)
+        if rank < len(b) - 1:
+            info["chunk"] = [float(sc.sigma[b[rank]]), float(sc.sigma[b[rank + 1]])]
+            rows, st, trk = S.run_chunk(P, mkprob, alg, cpf(np.sign(CONT["ds"]) * CONT["dsmax"]), P.norminf, sc, b[rank], b[rank + 1], s_total,
+                                        rank, rank == len(b) - 2, wrap_callback=tm.wrap)
+        else:
+            rows, st = [], None
+    ms = tm.total_ms()
+    ctx.sync()
+    torch.cuda.profiler.stop()
+    ctx.set_timing(False)
+    s1 = ctx.stats()
+    if st is not None:
+        info.update(rejected=int(st.nfail), work_newton=int(st.work_newton), work_linear=int(st.work_linear))
+    return rows, ms, {k: s1[k] - s0[k] for k in s1}, info
+
+
+def config_dict(n, workload, K, B, extra=None):
+    """Same keys in both arms (driver: same_config)."""
+    c = {"workload": workload, "grid": [n, n], "window": f"front branch from lambda = {PAR[0]} over PALC arclength {K * B * CONT['dsmax']:g} = {K} batches x {B} steps x dsmax {CONT['dsmax']:g}",
+         "batch": B, "newton_tol": 1e-9, "gmres": GMRES, "bls": BLS["kind"]}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def cpp_opts(cb, max_steps, workers):
+    return cb.make_opts(ds=CONT["ds"], dsmin=CONT["dsmin"], dsmax=CONT["dsmax"], p_min=CONT["p_min"], p_max=CONT["p_max"], max_steps=max_steps,
+                        newton_tol=1e-9, newton_maxit=15, reltol=GMRES["reltol"], restart=GMRES["restart"], maxiter=GMRES["maxiter"],
+                        pc_shift=1.0, nthreads=workers)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20, help="K: timed batches of --batch continuation steps")
+    ap.add_argument("--warmup", type=int, default=3, help="W: untimed continuation steps before the timed window")
     ap.add_argument("--grid", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=10, help="B: continuation steps (at dsmax) per bench step")
     ap.add_argument("--impl", default="bk200")
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--ref-batches", type=int, default=4, help="reference arm: bounded sample = the first batches of the window")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bls", default="matrixfree", choices=["matrixfree", "bordering"])
     ap.add_argument("--branch", default="front", choices=["front", "hexagons"])
     args = ap.parse_args()
-    n = args.grid
+    n, K, B = args.grid, args.steps, args.batch
     BLS["kind"] = args.bls
     BRANCH["kind"] = args.branch
     rank = int(os.environ.get("RANK", "0"))
@@ -270,40 +390,35 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"SH2d-fronts {n}x{n} fp64 on (lx, ly) = {n / 256:g} x (8 pi, 4 pi/sqrt 3), PALC (secant) + {'MatrixFreeBLS' if args.bls == 'matrixfree' else 'BorderingBLS'} + GMRES({GMRES['restart']}) reltol {GMRES['reltol']:g}, Pr = DCT (L1+I)^-1"
     cores = os.cpu_count() or 1
+    s_total = K * B * CONT["dsmax"]
+    metric = "continuation steps/sec (SH2d PALC)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        import scipy.fft  # noqa
-        # bounded sample: the CPU path needs a start point on the branch; the hexagon/front Newton solves at full
-        # size take minutes on CPU, so the sample starts from the front guess relaxed on the CPU with the same solver.
-        from oracle import problems, krylov, palc as opalc, precond as oprecond
+        # CPU restatement of the reference path in C++/OpenMP on all host cores (oracle/c); bounded sample: the first
+        # ref_batches batches of the same window, from the same start point (computed by the same CPU code)
+        from oracle import cbaseline as cb
         t_setup = time.perf_counter()
-        nthr, limiter = best_blas_threads(n * n, cores)
-        if limiter is not None:
-            limiter(limits=nthr, user_api="blas")
-
-        # (the BLAS thread count is calibrated BEFORE the start-up solves: with one BLAS thread per core of a 128-core host
-        # the two Newton solves below took 10 minutes, with the calibrated count about half a minute)
-        sh = problems.SwiftHohenberg((n, n), domain(n), l=PAR[0], nu=PAR[1])
-        Pinv = bordered_precond(oprecond.dct_precond((n, n), domain(n), 1.0, workers=cores), n * n)
-        ols = krylov.GMRESIterativeSolvers(N=n * n, Pr=Pinv, **GMRES)
-        prob = opalc.Problem(F=lambda u, l: sh.F(u, l), J=lambda u, l: (lambda v: sh.dF(u, v, l)), u0=sol0(n), p0=PAR[0])
-        hexa = opalc.newton(prob, prob.u0, PAR[0], opalc.NewtonPar(tol=1e-8, max_iterations=20, linsolver=ols), opalc.norminf)
-        fr = opalc.newton(prob, front_guess(hexa.u, n), PAR[0], opalc.NewtonPar(tol=1e-9, max_iterations=30, linsolver=ols),
-                          opalc.norminf)
-        assert fr.converged, fr.residuals
+        co = cpp_opts(cb, 1, 0)
+        hexa, ok, _, _ = cb.newton((n, n), domain(n), PAR[0], PAR[1], sol0(n), 1e-8, 20, co)
+        assert ok, "CPU Newton to the hexagons failed"
+        fr, ok, _, _ = cb.newton((n, n), domain(n), PAR[0], PAR[1], front_guess(hexa, n), 1e-9, 30, co)
+        assert ok, "CPU Newton to the front failed"
         t_setup = time.perf_counter() - t_setup
-        k = max(1, min(args.steps, args.cpu_steps))
-        rows, secs, nst = cpu_steps(n, fr.u, PAR[0], k, cores)
+        nb = max(1, min(K, args.ref_batches))
+        rows, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], fr, PAR[0], cpp_opts(cb, nb * B, 0))
+        nst = len(rows) - 1
         v = nst / secs
-        print(json.dumps({"metric": "continuation steps/sec (SH2d PALC)", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
-                          "steps": nst, "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-                          "config": {"workload": workload, "setup_s": round(t_setup, 1)},
-                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                           "sample": f"{nst} PALC steps from the converged front, NumPy/SciPy oracle (SciPy CSR SpMV 1 thread, "
-                                                     f"BLAS-1 on {getattr(cpu_steps, 'blas_threads', cores)} threads (calibrated), pocketfft DCT on {cores} threads)"},
+        thr = cb.load().bkcpu_max_threads()
+        print(json.dumps({"metric": metric, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * B / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "impl": "reference",
+                          "config": config_dict(n, workload, K, B, {"setup_s": round(t_setup, 1), "sample_steps": nst,
+                                                                    "corrector_work": {"newton_its": work[0], "linear_its": work[1]}}),
+                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": thr, "kind": "port",
+                                           "sample": f"the first {nst} continuation steps ({nb} of {K} batches) of the window from the converged front; "
+                                                     f"C++17/OpenMP restatement (oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads"},
                           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -320,134 +435,102 @@ def main():
     ctx, ls, u_front = gpu_setup(bk, n, dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
 
-    # ---- N > 1: the branch window of world*K steps is cut into interleaved sub-segments (segments.segment_starts); every
-    # rank gets its seed pairs from a deterministic scout run (replicated state; no state ever crosses NVLink)
-    plan = [(None, args.steps)]
-    scout_ms, scout_steps, grab = 0.0, 0, None
-    if world > 1:
-        P = bk.palc
-        plan = bk.segments.segment_starts(rank, world, args.steps)
-        grab = bk.segments.MultiSeedGrabber(plan, lambda v: v.copy())
-        cp = P.ContinuationPar(max_steps=grab.stop_at, newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=ls), **CONT)
-        prob = P.BifurcationProblemB200(ctx, u_front, PAR, lens=0)
-        sb = bk.MatrixFreeBLSB200(ls) if BLS["kind"] == "matrixfree" else bk.BorderingBLSB200(ls, check_precision=False)
-        tmark = []
-        ctx.sync()
-
-        def scout_cb(st):
-            if not tmark:
-                ctx.sync()
-                tmark.append(time.perf_counter())  # step 0: start of the continuation! loop
-            return grab(st)
-
-        _, sst = P.continuation(prob, P.PALC(bls=sb), cp, normC=P.norminf, callback=scout_cb)
-        ctx.sync()
-        scout_ms = (time.perf_counter() - tmark[0]) * 1e3
-        scout_steps = sst.step
+    # ---- warm-up: W untimed continuation steps from the start point (kernels, caches, allocator pools)
+    if args.warmup > 0:
+        gpu_run(bk, ctx, ls, u_front, PAR[0], args.warmup, 0, torch, timing=False, flush=flush)
 
     sampler = ClockSampler(dev)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    rows, ms, delta, nfail, wn, wl = [], [], {}, 0, 0, 0
-    for si, (a0, k) in enumerate(plan):
-        if a0 is None:
-            u_start, p_start, u1, p1 = u_front, PAR[0], None, None
-        else:
-            u_start, p_start, u1, p1 = grab.pair(a0)
-        r_, ms_, d_, st = gpu_run(bk, ctx, ls, u_start, p_start, k, args.warmup if si == 0 else 0, torch, timing=True, u1=u1, p1=p1,
-                                  flush=flush)
-        rows += r_ if si == 0 else r_[1:]
-        ms += ms_
-        for kk, vv in d_.items():
-            delta[kk] = delta.get(kk, 0) + vv
-        nfail, wn, wl = nfail + st.nfail, wn + st.work_newton, wl + st.work_linear
-    st.nfail, st.work_newton, st.work_linear = nfail, wn, wl
+    rows, my_ms, delta, info = window_job(bk, ctx, ls, n, u_front, s_total, rank, world, torch, flush)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     clocks = sampler.stop()
-    my_ms = float(np.sum(ms))
-    nsteps = len(ms)
-    tt = torch.tensor([my_ms, float(nsteps), scout_ms, float(scout_steps), float(st.nfail)], dtype=torch.float64, device=f"cuda:{dev}")
+    tt = torch.tensor([my_ms, float(len(rows)), info["scout_ms"], float(info["rejected"]), float(info["work_newton"]), float(info["work_linear"])],
+                      dtype=torch.float64, device=f"cuda:{dev}")
     if dist:
         allt = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(allt, tt)
         tmax = max(float(t[0]) for t in allt)
-        total_steps = int(sum(float(t[1]) for t in allt))
-        per_rank = [{"ms": round(float(t[0]), 1), "steps": int(t[1]), "rejected": int(t[4]), "scout_ms": round(float(t[2]), 1),
-                     "scout_steps": int(t[3])} for t in allt]
-        longest = max(allt, key=lambda t: float(t[3]))
-        scout_ms = float(longest[2])
-        same_window_1gpu = float(longest[3]) / (float(longest[2]) * 1e-3) if float(longest[2]) > 0 else None
-        # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear) per batch
-        gathered = bk.segments.all_gather_rows(rows, args.steps + args.warmup + 1, dist, torch, f"cuda:{dev}")
-        branch = bk.segments.merge_branch(gathered)
+        per_rank = [{"ms": round(float(t[0]), 1), "steps": int(t[1]), "scout_ms": round(float(t[2]), 1), "rejected": int(t[3])} for t in allt]
+        # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear)
+        gathered = bk.segments.all_gather_rows(rows, 4 * K * B + 64, dist, torch, f"cuda:{dev}")
+        branch = bk.segments.merge_chunks(gathered)
+        wn, wl = int(sum(float(t[4]) for t in allt)), int(sum(float(t[5]) for t in allt))
     else:
-        tmax, total_steps = my_ms, nsteps
-        per_rank, same_window_1gpu = None, None
+        tmax, per_rank = my_ms, None
         branch = np.array([[r["param"], r["x"], r["itnewton"], r["itlinear"]] for r in rows])
+        wn, wl = info["work_newton"], info["work_linear"]
+
+    # ---- e2e: the same job through the plugin / C ABI with HOST buffers (pinned NumPy state; H2D/D2H inside every call)
+    e2e = None
+    if not args.no_e2e:
+        nthr, limiter = best_blas_threads(n * n, cores)
+        if limiter is not None:
+            limiter(limits=nthr, user_api="blas")
+        ctx.pin_host = True
+        bk.palc.V.host_alloc = ctx.pinned_empty
+        uh = ctx.pinned_array(u_front.numpy())
+        if dist:
+            dist.barrier()
+        rows_h, ms_h, d_h, info_h = window_job(bk, ctx, ls, n, uh, s_total, rank, world, torch, flush, timing=False, wrap=ctx.pinned_array)
+        ctx.pin_host = False
+        bk.palc.V.host_alloc = None
+        th = torch.tensor([ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"])], dtype=torch.float64, device=f"cuda:{dev}")
+        if dist:
+            allh = [torch.zeros_like(th) for _ in range(world)]
+            dist.all_gather(allh, th)
+            tmax_h = max(float(t[0]) for t in allh)
+            h2d, d2h = sum(float(t[1]) for t in allh), sum(float(t[2]) for t in allh)
+        else:
+            tmax_h, h2d, d2h = ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"])
+        e2e = {"value": K * B / (tmax_h * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
+               "note": "the same window with pinned host NumPy state vectors: every residual / Jacobian / bordered solve crosses the C ABI with host pointers (H2D + D2H inside the timed region); bytes are per bench step (batch), all ranks"}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    value = total_steps / (tmax * 1e-3)
-    timed_rows = rows[args.warmup + 1:]
-    itn = float(np.mean([r["itnewton"] for r in timed_rows])) if timed_rows else 0.0
-    itl = float(np.mean([r["itlinear"] for r in timed_rows])) if timed_rows else 0.0
-
+    value = K * B / (tmax * 1e-3)
+    nst = len(branch)
     peak, peak_src = measured_peak()
     fused_ms, fused_b, fused_l = delta.get("total_fused_ms", 0.0), delta.get("total_fused_bytes", 0), delta.get("total_fused_launches", 0)
     ach = (fused_b / 1e9) / (fused_ms * 1e-3) if fused_ms > 0 else None
+    pc_ms, pc_n = delta.get("total_precond_ms", 0.0), delta.get("total_precond_applies", 0)
     roofline = {"bound": "hbm", "kernel": "k2_fused<E,bordered> + k2_update<E> (fused JVP+Arnoldi step = 2 launches per Krylov iteration; TMA ring)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src,
                 "traffic": ncu_traffic(), "launches": int(fused_l), "avg_launch_us": (fused_ms * 1e3 / fused_l) if fused_l else None,
                 "algorithmic_bytes_per_launch": (fused_b / fused_l) if fused_l else None,
-                "share_of_step": (fused_ms / my_ms) if my_ms else None}
+                "share_of_step": (fused_ms / my_ms) if my_ms else None,
+                "preconditioner": {"applies": int(pc_n), "avg_us": (pc_ms * 1e3 / pc_n) if pc_n else None, "share_of_step": (pc_ms / my_ms) if my_ms else None,
+                                   "algorithmic_bytes_per_apply": 3 * 16 * n * n}}
 
-    out = {"metric": "continuation steps/sec (SH2d PALC)", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": tmax / max(1, nsteps), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload, "grid": [n, n], "mean_itnewton": itn, "mean_itlinear_per_step": itl,
-                      "rejected_steps": int(st.nfail), "corrector_work": {"newton_its": int(st.work_newton), "linear_its": int(st.work_linear)},
-                      "l2": "256 MiB L2 flush between timed steps (outside the event pairs); Krylov basis per solve > L2",
-                      "parallelism": f"branch segments x{world}, replicated state" if world > 1 else "1 GPU",
-                      "scout_ms": scout_ms, "per_rank": per_rank,
-                      "same_window_1gpu_steps_per_s": same_window_1gpu,
-                      "scaling_note": ("N>1: the window of N*K steps reaches the snaking region of the branch, where one step costs ~4x the "
-                                       "first K steps that the N=1 run covers; same_window_1gpu_steps_per_s is one GPU (the scout) over the "
-                                       "same window") if world > 1 else None,
-                      "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())]},
-           "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline}
+    out = {"metric": metric, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+           "ms_per_step": tmax / max(1, K), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(n, workload, K, B, {
+               "continuation_steps_taken": int(nst - (1 if world == 1 else 0)), "mean_itnewton": float(np.mean(branch[1:, 2])) if nst > 1 else 0.0,
+               "mean_itlinear_per_step": float(np.mean(branch[1:, 3])) if nst > 1 else 0.0,
+               "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)},
+               "l2": "256 MiB L2 flush between continuation steps (outside the event pairs); Krylov basis per solve > L2",
+               "parallelism": (f"window cut into {world} chunks of equal predicted cost; replicated scout inside the timed region "
+                               f"(ds x{SCOUT['ds_factor']:g}, Newton tol {SCOUT['newton_tol']:g}, GMRES reltol {SCOUT['gmres_reltol']:g}); replicated state; "
+                               "all_gather of rows only") if world > 1 else "1 GPU",
+               "per_rank": per_rank, "scout_ms": info["scout_ms"], "scout_points": info["scout_points"],
+               "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())] if nst else None}),
+           "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline, "e2e": e2e}
 
-    # ---- e2e: the same steps through the plugin / C ABI with HOST buffers (NumPy state; H2D/D2H inside every call)
-    if not args.no_e2e and world == 1:
-        nthr, limiter = best_blas_threads(n * n, cores)
-        if limiter is not None:
-            limiter(limits=nthr, user_api="blas")
-        ctx.pin_host = True                      # host state lives in pinned (page-locked) NumPy arrays
-        bk.palc.V.host_alloc = ctx.pinned_empty
-        uh = ctx.pinned_array(u_front.numpy())
-        k_e2e = max(2, min(args.steps, 10))
-        rows_h, ms_h, d_h, _ = gpu_run(bk, ctx, ls, uh, PAR[0], k_e2e, 1, torch, timing=False, flush=flush)
-        ctx.pin_host = False
-        bk.palc.V.host_alloc = None
-        v = len(ms_h) / (np.sum(ms_h) * 1e-3)
-        out["e2e"] = {"value": v, "unit": "steps/s", "h2d_bytes_per_step": int(d_h["h2d_bytes"] / max(1, len(ms_h))),
-                      "d2h_bytes_per_step": int(d_h["d2h_bytes"] / max(1, len(ms_h))), "steps": len(ms_h),
-                      "note": "state vectors are pinned host NumPy arrays; every residual / Jacobian / bordered solve crosses the C ABI with host pointers (H2D + D2H inside the timed region)"}
-    elif world > 1:
-        out["e2e"] = None
-
-    # ---- cpu_baseline: oracle port on the host cores, bounded sample from the same start point
+    # ---- cpu_baseline: C++/OpenMP restatement on the host cores, bounded sample from the same start point
     if not args.no_cpu_baseline and world == 1:
-        rows_c, secs, nst = cpu_steps(n, u_front.numpy(), PAR[0], args.cpu_steps, cores)
-        out["cpu_baseline"] = {"value": nst / secs, "unit": "steps/s", "cores": cores, "kind": "port",
-                               "sample": f"{nst} PALC steps of the same branch from the same start point; "
-                                         f"NumPy/SciPy oracle: SciPy CSR SpMV with kron-assembled L1 (1 thread), BLAS-1 MGS on {getattr(cpu_steps, 'blas_threads', cores)} threads (calibrated), pocketfft DCT Pr ({cores} threads)"}
-        # parity of the sample rows with the GPU rows (same step history expected)
+        from oracle import cbaseline as cb
+        rows_c, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], u_front.numpy(), PAR[0], cpp_opts(cb, args.cpu_steps, 0))
+        nc = len(rows_c) - 1
+        thr = cb.load().bkcpu_max_threads()
+        out["cpu_baseline"] = {"value": nc / secs, "unit": "steps/s", "cores": thr, "kind": "port",
+                               "sample": f"the first {nc} continuation steps of the same window from the same start point; C++17/OpenMP restatement "
+                                         f"(oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads"}
         m = min(len(rows_c), len(rows))
         out["cpu_baseline"]["max_abs_param_diff_vs_gpu"] = float(max(abs(rows_c[i]["param"] - rows[i]["param"]) for i in range(m)))
     print(json.dumps(out))

@@ -24,6 +24,7 @@
 // Device check + timing: tools/fftcheck/fft_check.cu.
 #pragma once
 #include "bk_common.cuh"
+#include "bk_async.cuh"
 
 namespace bkf {
 
@@ -43,7 +44,7 @@ struct Cfg {
   static constexpr int TPSM = LOGE == 5 ? 256 : LOGE == 4 ? 512 : LOGE == 3 ? 768 : 1024;
   static constexpr int MINB = TPSM / THREADS > 0 ? TPSM / THREADS : 1;
   static constexpr int SLOTS = pad(N - 1) + 1;                     // padded complex slots per pair
-  static constexpr size_t SMEM = sizeof(double2) * (size_t)SLOTS * PP;
+  static constexpr size_t SMEM_DATA = sizeof(double2) * (size_t)SLOTS * PP;
   __host__ __device__ static constexpr int logr(int p) { return p < F ? LOGE : RB; }
   __host__ __device__ static constexpr int logNp(int p) { return LOGN - LOGE * p; }       // block length before pass p
   __host__ __device__ static constexpr int logMp(int p) { return logNp(p) - logr(p); }     // butterfly stride of pass p
@@ -53,6 +54,9 @@ struct Cfg {
     return o;
   }
   static constexpr int TW_TOTAL = tw_off(NP);
+  // shared memory: work array | twiddles | w_k | (lambda[k], lambda[n-k]) -- the tables are copied in by the TMA engine
+  static constexpr size_t SMEM = SMEM_DATA + sizeof(double2) * ((size_t)TW_TOTAL + N);          // forward / inverse kernels
+  static constexpr size_t SMEM_FUSED = SMEM + sizeof(double2) * (size_t)N;                      // fused kernel
   static_assert(LOGN >= LOGE + 1 && LOGN <= 11, "line length out of range");
   static_assert(THREADS <= 1024, "CTA too large");
 };
@@ -166,11 +170,35 @@ __device__ __forceinline__ void bfly_inv(double2 (&a)[ESZ]) {
 }
 
 // ------------------------------------------------------------------------------------------------ tables / geometry
-struct Tables {
+struct Tables {  // global memory (built on the host by build_tables)
   const double2* tw;    // per-pass contiguous forward twiddles  W_{N_p}^{b q} at tw_off(p) + (q-1) M' + b
   const double2* om;    // om[reg * T + tau]   = w_k          of the position the thread holds in register `reg` after the last pass
   const double2* lam2;  // lam2[reg * T + tau] = (lambda[k], lambda[(n-k) % n])
 };
+// Every table entry is read exactly once per line pair, by one thread: straight from global memory each read is an exposed L2
+// round trip (ncu, first version: long-scoreboard stalls 4.4 per issue at 3.5 warps per SM, 37 us for the fused kernel).  The
+// CTA therefore pulls its tables into shared memory with three bulk copies issued BEFORE griddepcontrol.wait -- the tables are
+// constants, so the copies overlap the tail of the previous kernel -- and waits on the mbarrier just before the first use.
+template <class C, bool FUSED>
+__device__ __forceinline__ Tables stage_tables(const Tables& g, double2* sm, unsigned long long* bar) {
+  Tables t;
+  double2* stw = sm + (size_t)C::SLOTS * C::PP;
+  double2* som = stw + C::TW_TOTAL;
+  double2* slam = som + C::N;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    constexpr unsigned twb = 16u * C::TW_TOTAL, nb = 16u * C::N;
+    mbar_arrive_expect_tx(bar, twb + nb + (FUSED ? nb : 0u));
+    if (twb) bulk_g2s(stw, g.tw, twb, bar);
+    bulk_g2s(som, g.om, nb, bar);
+    if (FUSED) bulk_g2s(slam, g.lam2, nb, bar);
+  }
+  t.tw = stw;
+  t.om = som;
+  t.lam2 = slam;
+  return t;
+}
 
 struct Geom {
   long long es;   // element stride along the line (doubles); 1 for contiguous lines
@@ -244,7 +272,7 @@ __device__ __forceinline__ void fwd_passes(double2 (&a)[C::E], double2* sm, cons
       for (int j = 0; j < R; ++j) {
         const int q = brev_c(j, LR);
         double2 v = a[u * R + j];
-        if (q > 0) v = cmul(v, __ldg(tw + ((q - 1) << LM) + b));
+        if (q > 0) v = cmul(v, tw[((q - 1) << LM) + b]);
         sm[slot<C>(base + (q << LM), pr)] = v;
       }
     }
@@ -268,7 +296,7 @@ __device__ __forceinline__ void inv_passes(double2 (&a)[C::E], double2* sm, cons
       for (int j = 0; j < R; ++j) {
         const int q = brev_c(j, LR);
         double2 v = sm[slot<C>(base + (q << LM), pr)];
-        if (q > 0) v = cmulc(v, __ldg(tw + ((q - 1) << LM) + b));
+        if (q > 0) v = cmulc(v, tw[((q - 1) << LM) + b]);
         a[u * R + j] = v;
       }
     }
@@ -341,11 +369,14 @@ __device__ __forceinline__ void strided_store(const double2 (&a)[C::E], double* 
 
 // MODE 0: forward (out = 2 C, natural k along the line), 1: inverse (out = n x from C), 2: forward, divide by the symbol, inverse
 template <class C, int MODE>
-static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, double* __restrict__ out, Geom g, Tables tb, Symbol sy) {
-  bk_pdl_sync();
-  extern __shared__ __align__(16) double2 sm_fast[];
+static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, double* __restrict__ out, Geom g, Tables tbg, Symbol sy) {
+  extern __shared__ __align__(128) double2 sm_fast[];
+  __shared__ __align__(8) unsigned long long tbar;
   double2* sm = sm_fast;
+  const Tables tb = stage_tables<C, MODE == 2>(tbg, sm, &tbar);
   const int tid = threadIdx.x, pr = tid % C::PP, tau = tid / C::PP;
+  __syncthreads();  // the barrier is initialised before anybody waits on it
+  bk_pdl_sync();
   const int col = (blockIdx.x * C::PP + pr) * 2, o = blockIdx.y;
   const bool v0 = col < g.nb, v1 = col + 1 < g.nb;
   const long long off = (long long)o * g.os + col;
@@ -353,6 +384,7 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
   double2 a[C::E];
   if (MODE != 1) {
     strided_load<C>(a, in + off, g.es, tau, v0, v1);
+    mbar_wait(&tbar, 0);
     fwd_passes<C, 0>(a, sm, tb, tau, pr);
     park<C>(a, sm, tau, pr);
     __syncthreads();
@@ -362,7 +394,7 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
     for (int reg = 0; reg < C::E; ++reg) {
       int k;
       const double2 z = a[reg], zp = partner<C>(sm, reg_pos<C>(tau, reg), pr, k);
-      const double2 w = __ldg(tb.om + reg * C::T + tau);
+      const double2 w = tb.om[reg * C::T + tau];
       const double sx = z.x + zp.x, sy_ = z.y - zp.y;   // Z + conj Zp
       const double dx = z.x - zp.x, dy = z.y + zp.y;    // Z - conj Zp
       // 2 C1 = Re(w (Z + conj Zp)),  2 C2 = Re(w (-i)(Z - conj Zp)) = w.x dy + w.y dx
@@ -381,6 +413,7 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
       const double* p = in + off + (long long)k * g.es;
       a[reg] = v1 ? __ldg(reinterpret_cast<const double2*>(p)) : make_double2(v0 ? __ldg(p) : 0.0, 0.0);
     }
+    mbar_wait(&tbar, 0);
     park<C>(a, sm, tau, pr);
     __syncthreads();
 #pragma unroll
@@ -388,7 +421,7 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
       int k;
       double2 dn = partner<C>(sm, reg_pos<C>(tau, reg), pr, k);
       if (k == 0) dn = make_double2(0.0, 0.0);
-      const double2 w = __ldg(tb.om + reg * C::T + tau);
+      const double2 w = tb.om[reg * C::T + tau];
       a[reg] = cmulc(make_double2(a[reg].x + dn.y, a[reg].y - dn.x), w);
     }
     __syncthreads();
@@ -400,8 +433,8 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
     for (int reg = 0; reg < C::E; ++reg) {
       int k;
       const double2 z = a[reg], zp = partner<C>(sm, reg_pos<C>(tau, reg), pr, k);
-      const double2 w = __ldg(tb.om + reg * C::T + tau);
-      const double2 l2 = __ldg(tb.lam2 + reg * C::T + tau);
+      const double2 w = tb.om[reg * C::T + tau];
+      const double2 l2 = tb.lam2[reg * C::T + tau];
       // A1 = w (Z + conj Zp) = 2 (C1[k] - i C1[n-k]),  A2 = w (-i)(Z - conj Zp) = 2 (C2[k] - i C2[n-k])
       const double2 A1 = cmul(make_double2(z.x + zp.x, z.y - zp.y), w);
       const double2 A2 = cmul(make_double2(z.y + zp.y, zp.x - z.x), w);
@@ -428,12 +461,15 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
 // MODE 0: forward, 1: inverse.  A CTA owns 2 PP consecutive lines; rows are staged in shared memory with coalesced 16-byte
 // accesses (the staging area aliases the FFT work array).
 template <class C, int MODE>
-static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, double* __restrict__ out, Geom g, Tables tb) {
-  bk_pdl_sync();
-  extern __shared__ __align__(16) double2 sm_fast[];
+static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, double* __restrict__ out, Geom g, Tables tbg) {
+  extern __shared__ __align__(128) double2 sm_fast[];
+  __shared__ __align__(8) unsigned long long tbar;
   double2* sm = sm_fast;
   double* st = reinterpret_cast<double*>(sm_fast);  // st[row * N + e]
+  const Tables tb = stage_tables<C, false>(tbg, sm, &tbar);
   const int tid = threadIdx.x, pr = tid % C::PP, tau = tid / C::PP;
+  __syncthreads();
+  bk_pdl_sync();
   const long long l0 = (long long)blockIdx.x * (2 * C::PP);
   constexpr int H = C::N / 2;
   for (int idx = tid; idx < 2 * C::PP * H; idx += C::THREADS) {
@@ -441,6 +477,7 @@ static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, dou
     const long long line = l0 + row;
     sm[idx] = (line < g.nb) ? __ldg(reinterpret_cast<const double2*>(in + line * g.os) + c2) : make_double2(0.0, 0.0);
   }
+  mbar_wait(&tbar, 0);
   __syncthreads();
   double2 a[C::E];
   const double* s1 = st + (2 * pr) * C::N;
@@ -459,7 +496,7 @@ static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, dou
     for (int reg = 0; reg < C::E; ++reg) {
       int k;
       const double2 z = a[reg], zp = partner<C>(sm, reg_pos<C>(tau, reg), pr, k);
-      const double2 w = __ldg(tb.om + reg * C::T + tau);
+      const double2 w = tb.om[reg * C::T + tau];
       const double sx = z.x + zp.x, sy_ = z.y - zp.y, dx = z.x - zp.x, dy = z.y + zp.y;
       a[reg] = make_double2(fma(w.x, sx, -(w.y * sy_)), fma(w.x, dy, w.y * dx));
     }
@@ -475,7 +512,7 @@ static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, dou
 #pragma unroll
     for (int reg = 0; reg < C::E; ++reg) {
       const int k = k_of_pos<C>(reg_pos<C>(tau, reg)), nk = (C::N - k) & (C::N - 1);
-      const double2 w = __ldg(tb.om + reg * C::T + tau);
+      const double2 w = tb.om[reg * C::T + tau];
       const double d1 = s1[k], d2 = s2[k];
       const double n1 = k ? s1[nk] : 0.0, n2 = k ? s2[nk] : 0.0;
       a[reg] = cmulc(make_double2(d1 + n2, d2 - n1), w);

@@ -210,8 +210,8 @@ static int fast_launch(bk_ctx* c, int d, bool strided, int mode, const double* i
       bk_ensure_smem(c, bkf::k_strided<FC, 1>, FC::SMEM);
       BK_CUDA(c, bk_launch_pdl(bkf::k_strided<FC, 1>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb, s0));
     } else {
-      bk_ensure_smem(c, bkf::k_strided<FC, 2>, FC::SMEM);
-      BK_CUDA(c, bk_launch_pdl(bkf::k_strided<FC, 2>, grid, dim3(FC::THREADS), FC::SMEM, c->stream, in, out, g, tb, s0));
+      bk_ensure_smem(c, bkf::k_strided<FC, 2>, FC::SMEM_FUSED);
+      BK_CUDA(c, bk_launch_pdl(bkf::k_strided<FC, 2>, grid, dim3(FC::THREADS), FC::SMEM_FUSED, c->stream, in, out, g, tb, s0));
     }
   } else {
     dim3 grid((unsigned)((g.nb + 2 * FC::PP - 1) / (2 * FC::PP)));

@@ -151,7 +151,7 @@ class Scout:
         self.points, self.sigma, self.cost, self.rows = [], [], [], []
 
 
-def run_scout(P, prob, alg, cp_scout, normC, s_total, copy, margin=0.0):
+def run_scout(P, prob, alg, cp_scout, normC, s_total, copy, margin=0.0, wrap_callback=None):
     """Loose continuation from the start point over arclength s_total (+ margin); returns a Scout."""
     V = P.V
     sc = Scout()
@@ -161,7 +161,8 @@ def run_scout(P, prob, alg, cp_scout, normC, s_total, copy, margin=0.0):
         return True
 
     trk = ArcTracker(V, alg.theta, 0.0, s_total + margin, on_point)
-    rows, st = P.continuation(prob, alg, cp_scout, normC=normC, callback=trk)
+    cb = wrap_callback(trk) if wrap_callback else trk  # e.g. bench.py's per-step CUDA-event timer
+    rows, st = P.continuation(prob, alg, cp_scout, normC=normC, callback=cb)
     sc.sigma = list(trk.sigma)
     sc.rows = rows[: len(sc.sigma)]
     # cost proxy of the interval ending at point j: its arclength (= number of full-accuracy steps at dsmax) weighted by
@@ -187,7 +188,7 @@ def partition_by_cost(cost, world, min_points=2):
     return b
 
 
-def run_chunk(P, make_prob, alg, cp, normC, sc, i0, i1, s_total, rank, last):
+def run_chunk(P, make_prob, alg, cp, normC, sc, i0, i1, s_total, rank, last, wrap_callback=None):
     """Full-accuracy PALC over the scout intervals (i0, i1]: two-point start from (z_i0, z_i0+1) -- rank 0 starts from the true
     start point the usual way -- until the curve passes seed i1 (or, for the last rank, the end of the window).
     Returns (rows, state); rows[0] (the seed itself) is dropped for rank > 0."""
@@ -212,11 +213,12 @@ def run_chunk(P, make_prob, alg, cp, normC, sc, i0, i1, s_total, rank, last):
         return proj < 0.0
 
     trk = ArcTracker(V, theta, s_start, np.inf, passed)
+    cb = wrap_callback(trk) if wrap_callback else trk
     if rank == 0 and i0 == 0:
-        rows, st = P.continuation(prob, alg, cp, normC=normC, callback=trk)
+        rows, st = P.continuation(prob, alg, cp, normC=normC, callback=cb)
         return rows, st, trk
     u1, p1 = sc.points[i0 + 1]
-    rows, st = P.continuation(prob, alg, cp, normC=normC, u1=u1, p1=p1, callback=trk)
+    rows, st = P.continuation(prob, alg, cp, normC=normC, u1=u1, p1=p1, callback=cb)
     return rows[1:], st, trk
 
 
