@@ -9,10 +9,13 @@ which the (lambda, ||u||) rows are exchanged, north_star); `value` = K * B / t i
 continuation step = secant predictor + Newton-Krylov corrector (per Newton iteration 2 residuals and one MatrixFreeBLS solve =
 one GMRES(100) with the DCT preconditioner on the right, fused JVP+Arnoldi kernels).  K = 20, B = 10 -> the 200-step branch.
 
-N = 1: plain continuation over the window.  N > 1: every rank runs a cheap, deterministic scout of the window itself
-(loose tolerances, larger steps; replicated state, nothing crosses NVLink), the window is cut into contiguous chunks of equal
-predicted cost, every rank advances its chunk at full accuracy from a scout seed pair (two-point start), and the rows are
-all_gathered.  The scout is INSIDE the timed region; the time of the job is the max over ranks.
+N = 1: plain continuation over the window (exactly K * B steps).  N > 1 ("replicas", SURVEY.md 8(e) / tier rule 5): PALC is a
+sequential recurrence, so one branch does not shard; every rank continues ITS OWN member of the front-branch family
+nu_r = nu (1 + 0.002 r) over the same window (independent continuation runs, replicated state, nothing crosses NVLink), the rows
+(lambda, ||u||, itnewton, itlinear) are all_gathered per job, `value` = N * K * B / max-over-ranks time, "scaling": "weak".
+The alternative `--partition scout` cuts ONE branch window into chunks seeded by a cheap scout inside the timed region
+(segments.py); measured on this branch it does not work -- a scout loose enough to be cheap leaves the snaking branch
+(profiles/r02_scout_probe.txt) -- so it is kept as an option, not the default.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 1024] [--batch 10] [--impl reference]
 
@@ -313,8 +316,9 @@ def make_algs(bk, ctx, ls, n):
 SCOUT = dict(ds_factor=4.0, newton_tol=1e-4, newton_maxit=8, gmres_reltol=1e-2)  # seed generator of the N > 1 partition (tools/scout_probe.py)
 
 
-def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timing=True, wrap=None):
-    """One rank's share of the window.  Returns (rows, ms, stats delta, info)."""
+def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timing=True, wrap=None, nsteps=None):
+    """One rank's job.  world == 1 (also every rank of the default "replicas" mode): exactly `nsteps` continuation steps from
+    u_start; world > 1: this rank's chunk of the arclength window s_total (--partition scout).  Returns (rows, ms, stats delta, info)."""
     P, S = bk.palc, bk.segments
     wrap = wrap or (lambda v: v)
     alg, cpf, alg_s, cps = make_algs(bk, ctx, ls, n)
@@ -326,8 +330,10 @@ def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timi
     torch.cuda.profiler.start()
     info = {"scout_ms": 0.0, "scout_points": 0, "chunk": None, "rejected": 0, "work_newton": 0, "work_linear": 0}
     if world == 1:
-        trk = S.ArcTracker(P.V, alg.theta, 0.0, s_total)
-        rows, st = P.continuation(mkprob(u_start, PAR[0]), alg, cpf(), normC=P.norminf, callback=tm.wrap(trk))
+        cp1 = cpf()
+        cp1.max_steps = nsteps
+        rows, st = P.continuation(mkprob(u_start, PAR[0]), alg, cp1, normC=P.norminf, callback=tm.wrap(None))
+        rows = rows[: nsteps + 1]
     else:
         tm.start()  # the scout's two start-up Newton solves are part of the job
         sc = S.run_scout(P, mkprob(u_start, PAR[0]), alg_s, cps, P.norminf, s_total, lambda v: wrap(v.copy() if hasattr(v, "copy") else v),
@@ -368,6 +374,7 @@ def cpp_opts(cb, max_steps, workers):
 
 
 def main():
+    global PAR
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20, help="K: timed batches of --batch continuation steps")
@@ -381,6 +388,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bls", default="matrixfree", choices=["matrixfree", "bordering"])
     ap.add_argument("--branch", default="front", choices=["front", "hexagons"])
+    ap.add_argument("--partition", default="replicas", choices=["replicas", "scout"], help="N > 1: independent branches (default) or one window cut by a scout")
     args = ap.parse_args()
     n, K, B = args.grid, args.steps, args.batch
     BLS["kind"] = args.bls
@@ -400,25 +408,26 @@ def main():
         # ref_batches batches of the same window, from the same start point (computed by the same CPU code)
         from oracle import cbaseline as cb
         t_setup = time.perf_counter()
-        co = cpp_opts(cb, 1, 0)
+        thr = cb.calibrated_threads(n * n)
+        co = cpp_opts(cb, 1, thr)
         hexa, ok, _, _ = cb.newton((n, n), domain(n), PAR[0], PAR[1], sol0(n), 1e-8, 20, co)
         assert ok, "CPU Newton to the hexagons failed"
         fr, ok, _, _ = cb.newton((n, n), domain(n), PAR[0], PAR[1], front_guess(hexa, n), 1e-9, 30, co)
         assert ok, "CPU Newton to the front failed"
         t_setup = time.perf_counter() - t_setup
         nb = max(1, min(K, args.ref_batches))
-        rows, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], fr, PAR[0], cpp_opts(cb, nb * B, 0))
+        rows, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], fr, PAR[0], cpp_opts(cb, nb * B, thr))
         nst = len(rows) - 1
         v = nst / secs
-        thr = cb.load().bkcpu_max_threads()
         print(json.dumps({"metric": metric, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * B / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "ms_per_step": 1e3 * B / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "impl": "reference",
                           "config": config_dict(n, workload, K, B, {"setup_s": round(t_setup, 1), "sample_steps": nst,
                                                                     "corrector_work": {"newton_its": work[0], "linear_its": work[1]}}),
                           "cpu_baseline": {"value": v, "unit": "steps/s", "cores": thr, "kind": "port",
                                            "sample": f"the first {nst} continuation steps ({nb} of {K} batches) of the window from the converged front; "
-                                                     f"C++17/OpenMP restatement (oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads"},
+                                                     f"C++17/OpenMP restatement (oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads "
+                                                     f"(fastest of the calibrated counts; the host offers {cb.load().bkcpu_max_threads()})"},
                           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -432,7 +441,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
-    ctx, ls, u_front = gpu_setup(bk, n, dev)
+    replicas = world > 1 and args.partition == "replicas"
+    nu_fallback = False
+    if replicas:
+        nu0 = PAR[1]
+        PAR = (PAR[0], nu0 * (1.0 + 0.002 * rank))  # this rank's member of the branch family
+        try:
+            ctx, ls, u_front = gpu_setup(bk, n, dev)
+        except AssertionError:
+            PAR, nu_fallback = (PAR[0], nu0), True   # no front at this nu: an identical replica of the nu_0 branch (flagged)
+            ctx, ls, u_front = gpu_setup(bk, n, dev)
+    else:
+        ctx, ls, u_front = gpu_setup(bk, n, dev)
+    jw = 1 if (replicas or world == 1) else world  # "world" seen by window_job
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
 
     # ---- warm-up: W untimed continuation steps from the start point (kernels, caches, allocator pools)
@@ -444,7 +465,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    rows, my_ms, delta, info = window_job(bk, ctx, ls, n, u_front, s_total, rank, world, torch, flush)
+    rows, my_ms, delta, info = window_job(bk, ctx, ls, n, u_front, s_total, rank, jw, torch, flush, nsteps=K * B)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -458,7 +479,7 @@ def main():
         per_rank = [{"ms": round(float(t[0]), 1), "steps": int(t[1]), "scout_ms": round(float(t[2]), 1), "rejected": int(t[3])} for t in allt]
         # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear)
         gathered = bk.segments.all_gather_rows(rows, 4 * K * B + 64, dist, torch, f"cuda:{dev}")
-        branch = bk.segments.merge_chunks(gathered)
+        branch = bk.segments.merge_chunks(gathered)  # replicas: the N branches one after the other
         wn, wl = int(sum(float(t[4]) for t in allt)), int(sum(float(t[5]) for t in allt))
     else:
         tmax, per_rank = my_ms, None
@@ -476,7 +497,7 @@ def main():
         uh = ctx.pinned_array(u_front.numpy())
         if dist:
             dist.barrier()
-        rows_h, ms_h, d_h, info_h = window_job(bk, ctx, ls, n, uh, s_total, rank, world, torch, flush, timing=False, wrap=ctx.pinned_array)
+        rows_h, ms_h, d_h, info_h = window_job(bk, ctx, ls, n, uh, s_total, rank, jw, torch, flush, timing=False, wrap=ctx.pinned_array, nsteps=K * B)
         ctx.pin_host = False
         bk.palc.V.host_alloc = None
         th = torch.tensor([ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"])], dtype=torch.float64, device=f"cuda:{dev}")
@@ -487,14 +508,14 @@ def main():
             h2d, d2h = sum(float(t[1]) for t in allh), sum(float(t[2]) for t in allh)
         else:
             tmax_h, h2d, d2h = ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"])
-        e2e = {"value": K * B / (tmax_h * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
+        e2e = {"value": (world if replicas else 1) * K * B / (tmax_h * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                "note": "the same window with pinned host NumPy state vectors: every residual / Jacobian / bordered solve crosses the C ABI with host pointers (H2D + D2H inside the timed region); bytes are per bench step (batch), all ranks"}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    value = K * B / (tmax * 1e-3)
+    value = (world if replicas else 1) * K * B / (tmax * 1e-3)
     nst = len(branch)
     peak, peak_src = measured_peak()
     fused_ms, fused_b, fused_l = delta.get("total_fused_ms", 0.0), delta.get("total_fused_bytes", 0), delta.get("total_fused_launches", 0)
@@ -509,15 +530,18 @@ def main():
                                    "algorithmic_bytes_per_apply": 3 * 16 * n * n}}
 
     out = {"metric": metric, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-           "ms_per_step": tmax / max(1, K), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "ms_per_step": tmax / max(1, K), "higher_is_better": True, "scaling": "weak" if (replicas or world == 1) else "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
            "config": config_dict(n, workload, K, B, {
-               "continuation_steps_taken": int(nst - (1 if world == 1 else 0)), "mean_itnewton": float(np.mean(branch[1:, 2])) if nst > 1 else 0.0,
+               "continuation_steps_taken": int(nst - (world if replicas else (1 if world == 1 else 0))), "mean_itnewton": float(np.mean(branch[1:, 2])) if nst > 1 else 0.0,
                "mean_itlinear_per_step": float(np.mean(branch[1:, 3])) if nst > 1 else 0.0,
                "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)},
                "l2": "256 MiB L2 flush between continuation steps (outside the event pairs); Krylov basis per solve > L2",
-               "parallelism": (f"window cut into {world} chunks of equal predicted cost; replicated scout inside the timed region "
-                               f"(ds x{SCOUT['ds_factor']:g}, Newton tol {SCOUT['newton_tol']:g}, GMRES reltol {SCOUT['gmres_reltol']:g}); replicated state; "
-                               "all_gather of rows only") if world > 1 else "1 GPU",
+               "parallelism": ("1 GPU" if world == 1 else
+                               (f"replicas only: {world} independent front branches nu_r = {1.3:g} (1 + 0.002 r), one per GPU, same window each; replicated "
+                                "state; all_gather of rows only" + ("; a rank fell back to nu_0" if nu_fallback else "")) if replicas else
+                               (f"one window cut into {world} chunks of equal predicted cost; replicated scout inside the timed region "
+                                f"(ds x{SCOUT['ds_factor']:g}, Newton tol {SCOUT['newton_tol']:g}, GMRES reltol {SCOUT['gmres_reltol']:g})")),
                "per_rank": per_rank, "scout_ms": info["scout_ms"], "scout_points": info["scout_points"],
                "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())] if nst else None}),
            "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline, "e2e": e2e}
@@ -525,12 +549,12 @@ def main():
     # ---- cpu_baseline: C++/OpenMP restatement on the host cores, bounded sample from the same start point
     if not args.no_cpu_baseline and world == 1:
         from oracle import cbaseline as cb
-        rows_c, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], u_front.numpy(), PAR[0], cpp_opts(cb, args.cpu_steps, 0))
+        thr = cb.calibrated_threads(n * n)
+        rows_c, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], u_front.numpy(), PAR[0], cpp_opts(cb, args.cpu_steps, thr))
         nc = len(rows_c) - 1
-        thr = cb.load().bkcpu_max_threads()
         out["cpu_baseline"] = {"value": nc / secs, "unit": "steps/s", "cores": thr, "kind": "port",
                                "sample": f"the first {nc} continuation steps of the same window from the same start point; C++17/OpenMP restatement "
-                                         f"(oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads"}
+                                         f"(oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads (calibrated; host offers {cb.load().bkcpu_max_threads()})"}
         m = min(len(rows_c), len(rows))
         out["cpu_baseline"]["max_abs_param_diff_vs_gpu"] = float(max(abs(rows_c[i]["param"] - rows[i]["param"]) for i in range(m)))
     print(json.dumps(out))

@@ -248,9 +248,13 @@ class GMRESB200:
     def __call__(self, J, rhs, rhs2=None, a0=0.0, a1=1.0):
         ctx = J.ctx
         if rhs2 is not None:
-            x1, ok1, it1 = self(J, rhs, a0=a0, a1=a1)
-            x2, ok2, it2 = self(J, rhs2, a0=a0, a1=a1)
-            return x1, x2, ok1 and ok2, (it1, it2)
+            # src/LinearSolver.jl:15-19: ls(J, rhs1, rhs2) -> (x1, x2, flag1 & flag2, (it1, it2)): one ABI crossing (bk_gmres2)
+            x1, x2 = ctx._like(rhs), ctx._like(rhs2)
+            o = self.opts()
+            cv = C.c_int32()
+            its = (C.c_int32 * 2)()
+            _chk(ctx, ctx.lib.bk_gmres2(ctx.handle, _l.ptr(rhs), _l.ptr(rhs2), _l.ptr(x1), _l.ptr(x2), a0, a1, C.byref(o), C.byref(cv), its))
+            return x1, x2, bool(cv.value), (its[0], its[1])
         x = ctx._like(rhs)
         o = self.opts()
         cv, it, rn = C.c_int32(), C.c_int32(), C.c_double()

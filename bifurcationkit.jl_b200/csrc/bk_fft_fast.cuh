@@ -2,7 +2,7 @@
 //
 // The preconditioner of the Swift-Hohenberg examples, (L1 + shift I)^-1 with L1 = (I + Lap_Neumann)^2
 // (examples/SH2d-fronts.jl:120-122, examples/SH3d.jl:88), is diagonal in the DCT-II basis (bk_precond.cu).  The second
-// generation (bk_dct.cuh, radix-4 passes IN shared memory) was instruction-bound: 6-12 M warp instructions per 2^20 points
+// generation (round 1: radix-4 passes IN shared memory) was instruction-bound: 6-12 M warp instructions per 2^20 points
 // and kernel, 0.10-0.17 of the HBM bound (profiles/r01c_ncu_k_dct2.csv).  This version keeps the data in registers:
 //
 //  * TWO real lines form ONE complex line z = v1 + i v2 after Makhoul's reordering (v[m] = x[2m], v[n-1-m] = x[2m+1]).  In

@@ -200,7 +200,8 @@ struct Sh2Scratch {
 // central 256 columns (16-byte aligned: x0 is a multiple of 256 and nx is even), issued by the producer lane and counted
 // on `tbar`; the 2 + 2 halo columns of every row are clamped scalar loads by 4 (E + 4) threads.  The stencil is linear in
 // v, so the deferred normalisation in_scale is applied to the results instead of the staged tile.
-template <int E, bool BORDERED>
+// RESID: the residual F(v) = -L1 v + l v + nu v^2 - v^3 (examples/SH2d-fronts.jl:31-34) instead of the JVP.
+template <int E, bool BORDERED, bool RESID = false>
 __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __restrict__ in, double in_scale, int x0, int y0,
                                               double* scratch, unsigned long long* tbar, double (&val)[E], double xp,
                                               double* bsum) {
@@ -248,9 +249,13 @@ __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __
       const double c0 = p[0];
       const double l1v = in_scale * (c0 + op.cx * (p[-1] - 2.0 * c0 + p[1]) + op.cy * (p[-S::QX] - 2.0 * c0 + p[S::QX]));
       const double v = in_scale * vs[(t + 2) + (e + 2) * S::VX];
-      const double uu = __ldg(op.u + gx + (long long)gy * nx);
-      const double coef = l + uu * (2.0 * nu - 3.0 * uu);
-      r = op.a0 * v + op.a1 * (coef * v - l1v);
+      if (RESID) {
+        r = v * (l + v * (nu - v)) - l1v;
+      } else {
+        const double uu = __ldg(op.u + gx + (long long)gy * nx);
+        const double coef = l + uu * (2.0 * nu - 3.0 * uu);
+        r = op.a0 * v + op.a1 * (coef * v - l1v);
+      }
       if (BORDERED) {
         const long long gi = gx + (long long)gy * nx;
         r += xp * __ldg(op.ba + gi) + op.bshift * v;
@@ -332,6 +337,36 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
   } else {
     __syncthreads();
     dots_finish(j, sred, scales, partials, counter, hcol, gcoef, &s_flag);
+  }
+}
+
+// Stand-alone K1 / K2 for the 2-D Swift-Hohenberg stencil on the same TMA-staged tile (MODE 0: out = a0 v + a1 J(u) v, 1: F(v)).
+// 256 columns x E rows per CTA, 16-byte aligned bulk rows, no per-element div/mod in the load phase.
+template <int E, int MODE>
+static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_apply(OpDesc op, const double* __restrict__ in,
+                                                                  const double* __restrict__ in_scale_ptr, double* __restrict__ out) {
+  extern __shared__ __align__(128) double smem2[];
+  __shared__ __align__(8) unsigned long long tbar;
+  if (threadIdx.x == 0) {
+    mbar_init(&tbar, 1);
+    fence_mbar_init();
+  }
+  const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
+  const int x0 = (blockIdx.x % tiles_x) * BK2_ROW, y0 = (blockIdx.x / tiles_x) * E;
+  const int rows = min(E, op.ny - y0), len = min(BK2_ROW, op.nx - x0);
+  __syncthreads();
+  const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
+  if (MODE == 0 && threadIdx.x == BK2_CONS) {
+    const unsigned row_b = (unsigned)(len * 8);
+    for (int r = 0; r < rows; ++r) bulk_prefetch_l2(op.u + x0 + (long long)(y0 + r) * op.nx, row_b);
+  }
+  double val[E];
+  double bsum = 0.0;
+  sh2_tile_eval<E, false, MODE == 1>(op, in, s, x0, y0, smem2, &tbar, val, 0.0, &bsum);
+  if (threadIdx.x < len) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < rows) out[x0 + (long long)(y0 + e) * op.nx + threadIdx.x] = val[e];
   }
 }
 

@@ -7,6 +7,7 @@
 //   bordered map src/LinearBorderSolver.jl:299-335
 #include "bk_common.cuh"
 #include "bk_stencil.cuh"
+#include "bk_krylov_tma.cuh"
 
 // ------------------------------------------------------------------------------------------ SH
 template <int DIM, int MODE>
@@ -296,6 +297,28 @@ template <int MODE>
 static int launch_kind(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* out) {
   switch (op.kind) {
     case BK_SH2D: {
+      const bool aligned = (op.nx % 2 == 0) && ((((uintptr_t)in) & 15) == 0);
+      static int no_tma = -1;
+      if (no_tma < 0) no_tma = getenv("BK_SH2D_NO_TMA") ? 1 : 0;  // diagnostics: the first-generation 64 x 32 tile kernel
+      if (aligned && !no_tma) {
+        // TMA-staged tile (bk_krylov_tma.cuh): tallest tile that still gives every SM about two CTAs
+        const int tiles_x = (op.nx + BK2_ROW - 1) / BK2_ROW;
+        int E = BK2_EMAX;
+        while (E > 1 && (long long)tiles_x * ((op.ny + E - 1) / E) < 2LL * c->nsm) E >>= 1;
+        const int grid = tiles_x * ((op.ny + E - 1) / E);
+#define BK2A_GO(EE)                                                                                        \
+  do {                                                                                                     \
+    const size_t sm = Sh2Scratch<EE>::BYTES;                                                               \
+    bk_ensure_smem(c, k2_apply<EE, MODE>, sm);                                                             \
+    k2_apply<EE, MODE><<<grid, BK2_THREADS, sm, c->stream>>>(op, in, sp, out);                             \
+  } while (0)
+        if (E == 8) BK2A_GO(8);
+        else if (E == 4) BK2A_GO(4);
+        else if (E == 2) BK2A_GO(2);
+        else BK2A_GO(1);
+#undef BK2A_GO
+        break;
+      }
       bk_ensure_smem(c, k_sh_apply<2, MODE>, ShSmem<2>::BYTES);
       k_sh_apply<2, MODE><<<sh_num_tiles<2>(op.nx, op.ny, 1), BK_THREADS, ShSmem<2>::BYTES, c->stream>>>(op, in, sp, out);
       break;

@@ -157,7 +157,15 @@ function (l::GMRESB200)(J::Jac, rhs; a₀ = VI.Zero(), a₁ = VI.One(), kwargs..
     cv[] == 0 && @debug "bk_gmres iterated maxiter = $(it[]) times without achieving the desired tolerance."
     return x, cv[] != 0, Int(it[])
 end
-# the generic two-rhs fallback (src/LinearSolver.jl:15-19) applies unchanged: ls(J, rhs1, rhs2) = two sequential solves.
+# two right-hand sides (src/LinearSolver.jl:15-19): one ABI crossing, (x1, x2, flag1 & flag2, (it1, it2))
+function (l::GMRESB200)(J::Jac, rhs1, rhs2; a₀ = VI.Zero(), a₁ = VI.One(), kwargs...)
+    c = J.ctx; o = Ref(opts(l))
+    x1, x2 = like(c, rhs1, length(rhs1)), like(c, rhs2, length(rhs2))
+    cv = Ref{Int32}(0); its = zeros(Int32, 2)
+    check(c, ccall((:bk_gmres2, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{GmresOpts}, Ptr{Int32}, Ptr{Int32}),
+                   c.handle, ptr(rhs1), ptr(rhs2), ptr(x1), ptr(x2), _num(a₀), _num(a₁), o, cv, its))
+    return x1, x2, cv[] != 0, (Int(its[1]), Int(its[2]))
+end
 
 # ---- AbstractBorderedLinearSolver (src/LinearBorderSolver.jl:1-6) ------------------------------------------------------
 Base.@kwdef struct BorderingBLSB200{S} <: BK.AbstractBorderedLinearSolver   # src/LinearBorderSolver.jl:59-166

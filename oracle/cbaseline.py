@@ -37,6 +37,13 @@ def load():
     return _lib
 
 
+def calibrated_threads(n):
+    """fastest OpenMP thread count for the MGS inner loop on vectors of length n (bkcpu_calibrate_threads)"""
+    lib = load()
+    lib.bkcpu_calibrate_threads.restype = C.c_int32
+    return int(lib.bkcpu_calibrate_threads(C.c_int64(n)))
+
+
 def make_opts(ds=-1e-3, dsmin=1e-4, dsmax=5e-3, p_min=-1.0, p_max=0.0, a=0.5, theta=0.5, eta=150.0, max_steps=5,
               newton_tol=1e-9, newton_maxit=15, reltol=1e-5, restart=100, maxiter=100, pc_shift=1.0, nthreads=0):
     return Opts(ds, dsmin, dsmax, p_min, p_max, a, theta, eta, max_steps, newton_tol, newton_maxit, reltol, restart, maxiter,

@@ -253,3 +253,29 @@ def test_gmres_many_waves_of_tall_tiles(bk, N):
         est = ls.last_resnorm / np.linalg.norm(b)
         assert ok and it <= 38, (orth, it, est, true)
         assert true < 2e-9 and abs(true - est) < 1e-3 * est + 1e-12, (orth, est, true)
+
+
+def test_gmres_two_right_hand_sides(bk):
+    """S2 (src/LinearSolver.jl:15-19): ls(J, rhs1, rhs2) -> (x1, x2, flag1 & flag2, (it1, it2)) through bk_gmres2, host and device
+    vectors, against two single solves and the oracle."""
+    from oracle import precond as oprecond
+    dims = (128, 64)
+    sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
+    rng = np.random.default_rng(11)
+    u = problems.sh2d_sol0(*dims, LX, LY)
+    r1, r2 = rng.standard_normal(sh.N), rng.standard_normal(sh.N)
+    ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=80, params=(-0.1, 1.3))
+    ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    ls = bk.GMRESB200(reltol=1e-9, restart=80, maxiter=80, Pr=True, orth="cgs2")
+    J = ctx.jacobian(u)
+    x1, x2, ok, (it1, it2) = ls(J, r1, r2, a0=1.5, a1=-1.0)
+    y1, ok1, j1 = ls(J, r1, a0=1.5, a1=-1.0)
+    y2, ok2, j2 = ls(J, r2, a0=1.5, a1=-1.0)
+    assert ok and ok1 and ok2 and (it1, it2) == (j1, j2)
+    assert np.array_equal(x1, y1) and np.array_equal(x2, y2)
+    Pinv = oprecond.dct_precond(dims, (LX, LY), 1.0)
+    ols = krylov.GMRESIterativeSolvers(reltol=1e-9, restart=80, maxiter=80, Pr=Pinv)
+    o1, o2, oko, _ = ols(lambda v: sh.dF(u, v), r1, r2, a0=1.5, a1=-1.0)
+    assert oko and _rel(x1, o1) < 1e-7 and _rel(x2, o2) < 1e-7
+    d1, d2, okd, itd = ls(ctx.jacobian(ctx.to_device(u)), ctx.to_device(r1), ctx.to_device(r2), a0=1.5, a1=-1.0)
+    assert okd and np.array_equal(d1.numpy(), x1) and np.array_equal(d2.numpy(), x2)
