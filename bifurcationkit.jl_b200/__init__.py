@@ -16,3 +16,4 @@ from . import segments
 from . import floquet
 from . import events
 from . import deflation
+from . import codim2

@@ -355,3 +355,56 @@ def test_hopf_point_located_by_bisection_on_device(bk):
     assert abs(bp.param - r_hopf) < 1e-5 and bp.delta == (2, 2) and bp.status == "converged"
     assert bp.interval[0] <= bp.param <= bp.interval[1] and bp.interval[1] - bp.interval[0] < 1e-4
     assert [row["n_unstable"] for row in br.rows][-1] == 2 and br.rows[0]["n_unstable"] == 0
+
+
+def test_newton_fold_on_device(bk):
+    """SURVEY 8f.3 (Fold half): minimally augmented Fold refinement (src/codim2/MinAugFold.jl:15-146,201-222) with device
+    vectors -- bordered solves through bk_bls_matrixfree / bk_bls_bordering, J' = J.  (i) Chan N = 101: same fold as the
+    host-array run with the oracle's dense bordered solver; (ii) SH2d hexagon branch (examples/SH2d-fronts.jl:88-92 continues it
+    through a fold near l = -0.215): the refined point has a singular Jacobian (smallest |eigenvalue| by shift-invert ~ 0)
+    and sits at the turning point of the branch."""
+    P = bk.palc
+    # (i) Chan
+    n, beta = 101, 0.01
+    ctx = bk.Context(bk.BK_CHAN, (n,), (1.0,), krylov_m=110, params=(3.3, beta))
+    ctx.precond_setup(bk.BK_PC_CHAN_TRIDIAG)
+    ls = bk.GMRESB200(reltol=1e-10, restart=110, maxiter=220, Pl=True, orth="cgs2")
+    bls = bk.MatrixFreeBLSB200(ls)
+    prob = P.BifurcationProblemB200(ctx, ctx.to_device(problems.chan_sol0(n)), (3.3, beta), lens=0)
+    pts = []
+    cp = P.ContinuationPar(dsmin=0.005, dsmax=0.1, ds=0.05, p_max=4.3, p_min=-1.0, max_steps=60,
+                           newton_options=P.NewtonPar(tol=1e-9, max_iterations=10, linsolver=ls))
+    P.continuation(prob, P.PALC(bls=bls), cp, callback=lambda st: pts.append((st.z_u.copy(), st.z_p, st.tau_u.copy())) or True)
+    ps = [p for _, p, _ in pts]
+    k = next(i for i in range(1, len(ps) - 1) if ps[i] > ps[i + 1])
+    x0, p0, tau = pts[k]
+    tau.scale_(1.0 / tau.norm())
+    sol = bk.codim2.newton_fold(prob, x0, p0, tau, tau, P.NewtonPar(tol=1e-8, max_iterations=12, linsolver=ls), bls)
+    assert sol.converged, sol.residuals
+    Fc = lambda x, a: problems.chan_F(x, a, beta)
+    Jc = lambda x, a: np.column_stack([problems.chan_dF(x, np.eye(n)[:, j], a, beta) for j in range(n)])
+    xf = sol.u.numpy()
+    sv = np.linalg.svd(Jc(xf, sol.p), compute_uv=False)
+    assert sv[-1] < 1e-5 * sv[0] and np.linalg.norm(Fc(xf, sol.p)) < 1e-7
+    assert p0 - 1e-9 <= sol.p < p0 + 0.02
+    # (ii) SH2d hexagons, 128 x 64
+    dims = (128, 64)
+    c2 = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=100, params=(-0.1, 1.3))
+    c2.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    l2 = bk.GMRESB200(reltol=1e-9, restart=100, maxiter=300, Pr=True, orth="cgs2")
+    b2 = bk.MatrixFreeBLSB200(l2)
+    pr2 = P.BifurcationProblemB200(c2, c2.to_device(problems.sh2d_sol0(*dims, LX, LY)), (-0.1, 1.3), lens=0)
+    pts = []
+    cp2 = P.ContinuationPar(dsmin=1e-4, dsmax=5e-3, ds=-1e-3, p_min=-1.0, p_max=0.0, max_steps=70,
+                            newton_options=P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=l2))
+    P.continuation(pr2, P.PALC(bls=b2), cp2, normC=P.norminf, callback=lambda st: pts.append((st.z_u.copy(), st.z_p, st.tau_u.copy())) or True)
+    ps = [p for _, p, _ in pts]
+    k = next((i for i in range(1, len(ps) - 1) if ps[i] < ps[i + 1]), None)   # l decreases to the fold, then increases
+    assert k is not None, ps
+    x0, p0, tau = pts[k]
+    tau.scale_(1.0 / tau.norm())
+    s2 = bk.codim2.newton_fold(pr2, x0, p0, tau, tau, P.NewtonPar(tol=1e-7, max_iterations=12, linsolver=l2), b2)
+    assert s2.converged, s2.residuals
+    assert p0 - 5e-3 < s2.p <= p0 + 1e-9                      # just beyond the smallest computed l
+    vals, _, cv, _ = bk.ShiftInvertB200(0.0, l2, krylovdim=30, tol=1e-8, maxrestart=10)(pr2.J(s2.u, s2.p), 1)
+    assert abs(vals[0]) < 1e-4, vals                           # singular Jacobian at the fold

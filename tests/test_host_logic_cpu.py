@@ -440,3 +440,46 @@ def test_deflated_newton_finds_the_three_chan_solutions():
     assert np.allclose(tops, [0.77197, 5.97988, 12.85103], atol=1e-4)
     for s in (s0, s1, s2):
         assert P.norminf(F(s.u, 3.3)) < 1e-8                  # roots of F itself, not only of M F
+
+
+# ------------------------------------------------------------------------------------------------ Fold minimally augmented
+def test_newton_fold_known_answers():
+    """newton_fold (src/codim2/MinAugFold.jl:15-146,201-222) on host arrays with the oracle's bordered solver:
+    (i) F = r + x - x^3 (test/continuation/test-cont-non-vector.jl:22-45): folds at x = +-1/sqrt(3), r = -+2/(3 sqrt 3);
+    (ii) a 2-D self-adjoint system with an analytic fold; (iii) the Chan problem (examples/chan.jl): the located point has a
+    singular Jacobian and sits at the turning point of the continuation branch."""
+    bk = g.load_package()
+    P = bk.palc
+    bls = BlsAdapter(obls.MatrixBLS())
+    opts = P.NewtonPar(tol=1e-10, max_iterations=12, linsolver=krylov.DefaultLS())
+    # (i)
+    F = lambda x, r: r + x - x**3
+    J = lambda x, r: np.diag(1 - 3 * x**2)
+    sol = bk.codim2.newton_fold(NumpyProblem(F, J, np.array([0.5]), -0.3), np.array([0.5]), -0.3, np.array([1.0]), np.array([1.0]), opts, bls)
+    assert sol.converged, sol.residuals
+    assert abs(sol.u[0] - 1 / np.sqrt(3)) < 1e-7 and abs(sol.p + 2 / (3 * np.sqrt(3))) < 1e-7 and abs(sol.sigma) < 1e-9
+    # (ii) x1: fold of p + x1 - x1^3 coupled symmetrically to a damped x2
+    F2 = lambda x, p: np.array([p + x[0] - x[0]**3 + 0.1 * x[1], 0.1 * x[0] - 2.0 * x[1]])
+    J2 = lambda x, p: np.array([[1 - 3 * x[0]**2, 0.1], [0.1, -2.0]])
+    s2 = bk.codim2.newton_fold(NumpyProblem(F2, J2, np.array([0.55, 0.03]), -0.35), np.array([0.55, 0.03]), -0.35, np.array([1.0, 0.0]),
+                               np.array([1.0, 0.0]), opts, bls)
+    assert s2.converged, s2.residuals
+    assert abs(np.linalg.det(J2(s2.u, s2.p))) < 1e-8 and np.linalg.norm(F2(s2.u, s2.p)) < 1e-9
+    # (iii) Chan: continuation through the fold, then refine the turning point
+    n, beta = 31, 0.01
+    Fc = lambda x, a: problems.chan_F(x, a, beta)
+    Jc = lambda x, a: np.column_stack([problems.chan_dF(x, np.eye(n)[:, k], a, beta) for k in range(n)])
+    pts = []
+    cp = P.ContinuationPar(dsmin=0.005, dsmax=0.1, ds=0.05, p_max=4.3, p_min=-1.0, max_steps=120,
+                           newton_options=P.NewtonPar(tol=1e-10, max_iterations=10, linsolver=krylov.DefaultLS()))
+    rows, _ = P.continuation(NumpyProblem(Fc, Jc, problems.chan_sol0(n), 3.3), P.PALC(bls=bls), cp,
+                             callback=lambda st: pts.append((st.z_u.copy(), st.z_p, st.tau_u.copy())) or True)
+    ps = [p for _, p, _ in pts]
+    k = next(i for i in range(1, len(ps) - 1) if ps[i] > ps[i + 1])  # first turning point of the S-shaped branch
+    assert 0 < k < len(pts) - 1
+    x0, p0, tau = pts[k]
+    s3 = bk.codim2.newton_fold(NumpyProblem(Fc, Jc, x0, p0), x0, p0, tau / np.linalg.norm(tau), tau / np.linalg.norm(tau), opts, bls)
+    assert s3.converged, s3.residuals
+    sv = np.linalg.svd(Jc(s3.u, s3.p), compute_uv=False)
+    assert sv[-1] < 1e-6 * sv[0] and np.linalg.norm(Fc(s3.u, s3.p)) < 1e-8
+    assert p0 - 1e-9 <= s3.p < p0 + 0.02                          # the true fold lies at or just beyond the largest computed parameter
