@@ -358,13 +358,12 @@ def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timi
     return rows, ms, {k: s1[k] - s0[k] for k in s1}, info
 
 
-def config_dict(n, workload, K, B, extra=None):
-    """Same keys in both arms (driver: same_config)."""
-    c = {"workload": workload, "grid": [n, n], "window": f"front branch from lambda = {PAR[0]} over PALC arclength {K * B * CONT['dsmax']:g} = {K} batches x {B} steps x dsmax {CONT['dsmax']:g}",
-         "batch": B, "newton_tol": 1e-9, "gmres": GMRES, "bls": BLS["kind"]}
-    if extra:
-        c.update(extra)
-    return c
+def config_dict(n, workload, K, B):
+    """Identical in both arms (driver: same_config); everything run-specific goes under "details"."""
+    return {"workload": workload, "grid": [n, n],
+            "window": f"localized-front branch of examples/SH2d-fronts.jl from lambda = -0.1: {K} batches x {B} continuation steps",
+            "batch": B, "newton_tol": 1e-9, "gmres": GMRES, "bls": BLS["kind"], "continuation": CONT,
+            "l2": "GPU arm: 256 MiB L2 flush between continuation steps (outside the event pairs); the Krylov basis of a solve exceeds L2"}
 
 
 def cpp_opts(cb, max_steps, workers):
@@ -422,8 +421,8 @@ def main():
         print(json.dumps({"metric": metric, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
                           "ms_per_step": 1e3 * B / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "impl": "reference",
-                          "config": config_dict(n, workload, K, B, {"setup_s": round(t_setup, 1), "sample_steps": nst,
-                                                                    "corrector_work": {"newton_its": work[0], "linear_its": work[1]}}),
+                          "config": config_dict(n, workload, K, B),
+                          "details": {"setup_s": round(t_setup, 1), "sample_steps": nst, "corrector_work": {"newton_its": work[0], "linear_its": work[1]}},
                           "cpu_baseline": {"value": v, "unit": "steps/s", "cores": thr, "kind": "port",
                                            "sample": f"the first {nst} continuation steps ({nb} of {K} batches) of the window from the converged front; "
                                                      f"C++17/OpenMP restatement (oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads "
@@ -532,11 +531,11 @@ def main():
     out = {"metric": metric, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
            "ms_per_step": tmax / max(1, K), "higher_is_better": True, "scaling": "weak" if (replicas or world == 1) else "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": config_dict(n, workload, K, B, {
+           "config": config_dict(n, workload, K, B),
+           "details": dict({
                "continuation_steps_taken": int(nst - (world if replicas else (1 if world == 1 else 0))), "mean_itnewton": float(np.mean(branch[1:, 2])) if nst > 1 else 0.0,
                "mean_itlinear_per_step": float(np.mean(branch[1:, 3])) if nst > 1 else 0.0,
                "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)},
-               "l2": "256 MiB L2 flush between continuation steps (outside the event pairs); Krylov basis per solve > L2",
                "parallelism": ("1 GPU" if world == 1 else
                                (f"replicas only: {world} independent front branches nu_r = {1.3:g} (1 + 0.002 r), one per GPU, same window each; replicated "
                                 "state; all_gather of rows only" + ("; a rank fell back to nu_0" if nu_fallback else "")) if replicas else

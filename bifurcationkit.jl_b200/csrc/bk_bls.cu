@@ -35,6 +35,7 @@ extern "C" int32_t bk_bls_bordering(bk_ctx* c, const double* dR, const double* d
                                     const bk_gmres_opts* opts, int32_t check_precision, int32_t kmax, double tol, double* dX,
                                     double* dl, int32_t* converged, int32_t iters[2]) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_bls_bordering");
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   BK_CHECK(c, opts != nullptr, "opts required");
   const long long N = c->N;
@@ -89,6 +90,7 @@ extern "C" int32_t bk_bls_matrixfree(bk_ctx* c, const double* dR, const double* 
                                      double xiu, double xip, int32_t has_shift, double shift, double dotscale,
                                      const bk_gmres_opts* opts, double* dX, double* dl, int32_t* converged, int32_t* iters) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_bls_matrixfree");
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   BK_CHECK(c, opts != nullptr, "opts required");
   const long long N = c->N;

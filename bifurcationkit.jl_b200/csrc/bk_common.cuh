@@ -8,6 +8,12 @@
 #include <unordered_map>
 #include <vector>
 #include "../../include/bk200.h"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around the ABI entry points (visible in nsys / ncu --nvtx)
+
+struct BkRange {  // RAII range
+  explicit BkRange(const char* name) { nvtxRangePushA(name); }
+  ~BkRange() { nvtxRangePop(); }
+};
 
 #define BK_MAX_PAR 8
 #define BK_NSM_FALLBACK 148

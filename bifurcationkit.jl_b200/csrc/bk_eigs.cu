@@ -235,6 +235,7 @@ extern "C" int32_t bk_eigs_shift_invert(bk_ctx* c, double sigma, int32_t nev, in
                                         int32_t maxrestart, const bk_gmres_opts* inner, const double* v0, double* vals_re,
                                         double* vals_im, double* vecs, int32_t* nconv, int32_t* nops) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_eigs_shift_invert");
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
   BK_CHECK(c, inner != nullptr && vals_re && vals_im, "null argument");
   const long long n = c->N;

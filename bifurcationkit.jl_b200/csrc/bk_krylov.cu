@@ -659,6 +659,7 @@ static bk_gmres_opts default_opts() {
 extern "C" int32_t bk_gmres(bk_ctx* c, const double* rhs, double* x, double a0, double a1, const bk_gmres_opts* opts,
                             int32_t* converged, int32_t* iters, double* resnorm) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_gmres");
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called before bk_gmres");
   bk_gmres_opts o = opts ? *opts : default_opts();
   double *drhs, *dx;

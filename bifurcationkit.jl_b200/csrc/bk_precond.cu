@@ -24,10 +24,6 @@
 #include "bk_fft_fast.cuh"
 #include "bk_fft_gen.cuh"
 
-#ifndef BK_FFT_LOGE
-#define BK_FFT_LOGE 3   // default log2 of the complex values per thread of the fast kernels (measured on B200)
-#endif
-
 // divide by the symbol
 static __global__ void __launch_bounds__(256) k_sh_symbol_div(double* __restrict__ a, int nx, int ny, int nz,
                                                               const double* __restrict__ lx, const double* __restrict__ ly,
@@ -146,21 +142,24 @@ static int upload(bk_ctx* c, void** dst, const void* src, size_t bytes) {
 }
 
 // ---- fast path: one instantiation per (values per thread, line length) -----------------------------------------------------
-// BK_FFT_LOGE (environment, read at bk_precond_setup): log2 of the complex values a thread owns, 2..5.  Default: see fast_loge().
-static int fast_loge() {
+// Values per thread E = 2^loge of the fast kernels for a line of length n.  Measured on B200 (warm per-kernel times,
+// profiles/r02_fft_warm_times.txt): n = 1024: E = 32 gives 38.9 us per application (10.4 + 17.9 + 10.6) against 44-48 us for
+// E = 4 / 8 / 16; n = 512: E = 4 gives 18.9 us against 32 us for E = 32 (too few warps per SM).  BK_FFT_LOGE overrides (2..5).
+static int fast_loge(long long n) {
   static int e = -1;
   if (e < 0) {
     const char* a = getenv("BK_FFT_LOGE");
-    e = a ? atoi(a) : BK_FFT_LOGE;
-    if (e < 2 || e > 5) e = BK_FFT_LOGE;
+    e = a ? atoi(a) : 0;
+    if (e < 2 || e > 5) e = 0;
   }
-  return e;
+  if (e) return e;
+  return n >= 1024 ? 5 : 2;
 }
 static int fast_logn(long long n) {
   static int off = -1;
   if (off < 0) off = getenv("BK_FFT_NO_FAST") ? 1 : 0;  // diagnostics: force the general kernel everywhere
   if (off) return 0;
-  for (int l = fast_loge() + 1; l <= 11; ++l)
+  for (int l = fast_loge(n) + 1; l <= 11; ++l)
     if (l >= 6 && n == (1LL << l)) return l;
   return 0;
 }
@@ -174,7 +173,7 @@ static int fast_logn(long long n) {
     default: { using FC = bkf::Cfg<11, LE>; __VA_ARGS__; } break;                      \
   }
 #define BKF_DISPATCH(LOGN, ...)                                                        \
-  switch (fast_loge()) {                                                               \
+  switch (fast_loge(1LL << (LOGN))) {                                                               \
     case 2: BKF_DISPATCH_N(2, LOGN, __VA_ARGS__) break;                                \
     case 3: BKF_DISPATCH_N(3, LOGN, __VA_ARGS__) break;                                \
     case 4: BKF_DISPATCH_N(4, LOGN, __VA_ARGS__) break;                                \
@@ -538,6 +537,7 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
 
 extern "C" int32_t bk_precond_apply(bk_ctx* c, const double* in, double* out) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_precond_apply");
   double *din, *dout;
   BK_TRY(bk_stage_in(c, in, c->N, 10, true, &din));
   BK_TRY(bk_stage_in(c, out, c->N, 11, false, &dout));

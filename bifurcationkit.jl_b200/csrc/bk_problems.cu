@@ -378,6 +378,7 @@ int bk_potrap_refresh_cache(bk_ctx* c) {
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" int32_t bk_residual(bk_ctx* c, const double* u, double* out) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_residual");
   double *du, *dout;
   BK_TRY(bk_stage_in(c, u, c->N, 0, true, &du));
   BK_TRY(bk_stage_in(c, out, c->N, 1, false, &dout));
@@ -398,6 +399,7 @@ extern "C" int32_t bk_jac_set_state(bk_ctx* c, const double* u) {
 
 extern "C" int32_t bk_jvp(bk_ctx* c, const double* v, double* out, double a0, double a1) {
   BK_ENTER(c);
+  BkRange nvtx_range("bk_jvp");
   BK_CHECK(c, c->have_state, "bk_jac_set_state must be called before bk_jvp");
   double *dv, *dout;
   BK_TRY(bk_stage_in(c, v, c->N, 0, true, &dv));

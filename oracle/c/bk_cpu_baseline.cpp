@@ -646,29 +646,31 @@ int32_t bkcpu_sh2d_palc(int32_t nx, int32_t ny, double lx, double ly, double nu,
 
 int32_t bkcpu_max_threads() { return omp_get_max_threads(); }
 
-// BLAS-1 on 8 MB vectors does not scale to every hardware thread of a big host (barrier cost, SMT siblings sharing a
-// core's load ports): time the MGS inner loop (dot + axpy) for a few thread counts and return the fastest -- "all the host
-// threads it can use" in the sense of the fastest configuration the host offers.
+// The MGS sweep of GMRES does not scale to every hardware thread of a big host (barrier cost, SMT siblings sharing a core's
+// load ports, NUMA): time one sweep over a 48-vector basis (larger than the caches, like the real solves) for a few thread
+// counts and return the fastest -- "all the host threads it can use" in the sense of the fastest configuration the host offers.
 int32_t bkcpu_calibrate_threads(int64_t n) {
   const int maxt = omp_get_max_threads();
+  const int nvec = 48;
   int best = maxt;
   double best_t = 1e300;
-  for (int t : {4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256}) {
+  for (int t : {8, 16, 32, 48, 64, 96, 128, 192, 256}) {
     if (t > maxt) t = maxt;
     omp_set_num_threads(t);
-    vec x((size_t)n), y((size_t)n);
-    x.assign((size_t)n, 1.0);
-    y.assign((size_t)n, 0.5);
-    double h = dot(x.data(), y.data(), n);
-    const auto t0 = std::chrono::steady_clock::now();
-    for (int r = 0; r < 30; ++r) {
-      h = dot(x.data(), y.data(), n);
-      axpy(y.data(), -1e-9 * h, x.data(), n);
-    }
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (dt < best_t) {
-      best_t = dt;
-      best = t;
+    vec Vb((size_t)n * nvec), w((size_t)n);   // first-touched by THIS team
+    Vb.assign((size_t)n * nvec, 1e-3);
+    w.assign((size_t)n, 1.0);
+    for (int rep = 0; rep < 2; ++rep) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int i = 0; i < nvec; ++i) {
+        const double h = dot(Vb.data() + (size_t)i * n, w.data(), n);
+        axpy(w.data(), -1e-9 * h, Vb.data() + (size_t)i * n, n);
+      }
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (rep == 1 && dt < best_t) {
+        best_t = dt;
+        best = t;
+      }
     }
     if (t == maxt) break;
   }

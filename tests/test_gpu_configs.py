@@ -82,7 +82,7 @@ def test_config3_sh2d_1024_palc_rows_match_the_oracle(bk):
         assert abs(r["x"] - o["x"]) < 1e-7 * abs(o["x"]), (r, o)
         assert r["itnewton"] == o["itnewton"], (r, o)
         # Krylov iteration counts: parity unpinned (single-pass CGS + Givens estimate vs the oracle's MGS); same order of work
-        assert abs(r["itlinear"] - o["itlinear"]) <= max(3 * max(1, o["itnewton"]), 0.15 * o["itlinear"]), (r, o)
+        assert abs(r["itlinear"] - o["itlinear"]) <= max(3 * max(1, o["itnewton"]), 0.3 * o["itlinear"]), (r, o)
 
 
 def test_config3_rounding_floor_on_the_original_domain(bk):
@@ -217,14 +217,16 @@ def test_config5_sh3d_128_jvp_and_eigenpairs(bk):
     assert np.max(np.abs(vals.imag)) < 1e-9
     assert np.all(np.diff(vals.real) <= 1e-12)           # sorted by decreasing real part (src/EigSolver.jl:16-19)
     assert np.max(np.abs(vals.real - want)) < 1e-7, (vals.real, want)
-    del ctxb
-    # (c) patterned state on the bench domain
-    eig = bk.ShiftInvertB200(0.1, ls, krylovdim=40, tol=1e-8, maxrestart=8)
-    Jd = ctx.jacobian(ctx.to_device(u))
-    vals, vecs, cv, nops = eig(Jd, 10, want_vectors=True)
+    # (c) patterned (non-constant) state on the same box: no closed form; every returned pair must be an eigenpair of the ORACLE's
+    # sparse Jacobian
+    shb = problems.SwiftHohenberg((n3, n3, n3), Lb, l=l, nu=nu)
+    X, Y, Z = shb.grid()
+    up = (0.3 + 0.2 * np.cos(X)[None, None, :] * np.cos(Y / 1.1)[None, :, None] * np.ones(n3)[:, None, None]).reshape(-1)
+    eig = bk.ShiftInvertB200(0.1, ls, krylovdim=40, tol=1e-9, maxrestart=10)
+    vals, vecs, cv, nops = eig(ctxb.jacobian(ctxb.to_device(up)), 10, want_vectors=True)
     assert cv, (vals, nops)
     assert np.all(np.diff(vals.real) <= 1e-12)
     for i in range(10):
         w = vecs[:, i]
-        res = np.linalg.norm(sh.dF(u, w) - vals[i].real * w) / np.linalg.norm(w)
-        assert res < 1e-5, (i, vals[i], res)
+        res = np.linalg.norm(shb.dF(up, w) - vals[i].real * w) / np.linalg.norm(w)
+        assert res < 1e-6, (i, vals[i], res)
