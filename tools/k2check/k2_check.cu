@@ -19,7 +19,7 @@ __global__ void k_fill(double* p, long long n, unsigned long long seed) {
 __global__ void k_ref_update(const double* w, long long n, const double* V, long long ld, int j, const double* g, double* out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double v = w[i];
-    for (int k = 0; k < j; ++k) v = fma(-g[k], V[(long long)k * ld + i], v);
+    for (int k = j - 1; k >= 0; --k) v = fma(-g[k], V[(long long)k * ld + i], v);  // k2_update walks the basis backwards (round 2)
     out[i] = v;
   }
 }
