@@ -9,10 +9,12 @@ which the (lambda, ||u||) rows are exchanged, north_star); `value` = K * B / t i
 continuation step = secant predictor + Newton-Krylov corrector (per Newton iteration 2 residuals and one MatrixFreeBLS solve =
 one GMRES(100) with the DCT preconditioner on the right, fused JVP+Arnoldi kernels).  K = 20, B = 10 -> the 200-step branch.
 
-N = 1: plain continuation over the window (exactly K * B steps).  N > 1 ("replicas", SURVEY.md 8(e) / tier rule 5): PALC is a
-sequential recurrence, so one branch does not shard; every rank continues ITS OWN member of the front-branch family
-nu_r = nu (1 + 0.002 r) over the same window (independent continuation runs, replicated state, nothing crosses NVLink), the rows
-(lambda, ||u||, itnewton, itlinear) are all_gathered per job, `value` = N * K * B / max-over-ranks time, "scaling": "weak".
+N = 1: plain continuation over the window (exactly K * B steps).  N > 1 ("replicas only", SURVEY.md 8(e) / tier rule 5): PALC is a
+sequential recurrence, so one branch does not shard; every rank runs an independent replica of the same job (replicated state,
+nothing crosses NVLink), the rows (lambda, ||u||, itnewton, itlinear) are all_gathered per job -- and must agree bit for bit
+across the GPUs, which the JSON reports -- `value` = N * K * B / max-over-ranks time, "scaling": "weak".  (A family of branches
+nu_r = nu (1 + 0.002 r) was tried first: at nu_1 the same start-up already lands on a different, 30x cheaper branch, so the
+ranks would not do comparable work.)
 The alternative `--partition scout` cuts ONE branch window into chunks seeded by a cheap scout inside the timed region
 (segments.py); measured on this branch it does not work -- a scout loose enough to be cheap leaves the snaking branch
 (profiles/r02_scout_probe.txt) -- so it is kept as an option, not the default.
@@ -313,6 +315,9 @@ def make_algs(bk, ctx, ls, n):
     return alg, cp, P.PALC(bls=mkbls(ls_s)), cps
 
 
+TIMING_EVERY = 8  # roofline sampling: the event records sit between PDL launches, so timing every solve would slow the step it measures
+
+
 SCOUT = dict(ds_factor=4.0, newton_tol=1e-4, newton_maxit=8, gmres_reltol=1e-2)  # seed generator of the N > 1 partition (tools/scout_probe.py)
 
 
@@ -325,7 +330,7 @@ def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timi
     mkprob = lambda u, p: P.BifurcationProblemB200(ctx, u, [p] + list(PAR[1:]), lens=0)
     tm = StepTimer(ctx, torch, flush)
     ctx.sync()
-    ctx.set_timing(timing)
+    ctx.set_timing(TIMING_EVERY if timing else 0)  # CUDA-event pairs around the fused kernels of every TIMING_EVERY-th solve
     s0 = ctx.stats()
     torch.cuda.profiler.start()
     info = {"scout_ms": 0.0, "scout_points": 0, "chunk": None, "rejected": 0, "work_newton": 0, "work_linear": 0}
@@ -441,17 +446,7 @@ def main():
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
     replicas = world > 1 and args.partition == "replicas"
-    nu_fallback = False
-    if replicas:
-        nu0 = PAR[1]
-        PAR = (PAR[0], nu0 * (1.0 + 0.002 * rank))  # this rank's member of the branch family
-        try:
-            ctx, ls, u_front = gpu_setup(bk, n, dev)
-        except AssertionError:
-            PAR, nu_fallback = (PAR[0], nu0), True   # no front at this nu: an identical replica of the nu_0 branch (flagged)
-            ctx, ls, u_front = gpu_setup(bk, n, dev)
-    else:
-        ctx, ls, u_front = gpu_setup(bk, n, dev)
+    ctx, ls, u_front = gpu_setup(bk, n, dev)
     jw = 1 if (replicas or world == 1) else world  # "world" seen by window_job
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
 
@@ -471,6 +466,7 @@ def main():
     clocks = sampler.stop()
     tt = torch.tensor([my_ms, float(len(rows)), info["scout_ms"], float(info["rejected"]), float(info["work_newton"]), float(info["work_linear"])],
                       dtype=torch.float64, device=f"cuda:{dev}")
+    replica_dev = None
     if dist:
         allt = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(allt, tt)
@@ -479,6 +475,9 @@ def main():
         # the path's only collective: all_gather of the branch rows (lambda, ||u||, itnewton, itlinear)
         gathered = bk.segments.all_gather_rows(rows, 4 * K * B + 64, dist, torch, f"cuda:{dev}")
         branch = bk.segments.merge_chunks(gathered)  # replicas: the N branches one after the other
+        if replicas:  # determinism across GPUs: every replica must produce the same rows
+            g0 = gathered[0]
+            replica_dev = float(max(np.nanmax(np.abs(np.nan_to_num(gr[:, :2]) - np.nan_to_num(g0[:, :2]))) for gr in gathered))
         wn, wl = int(sum(float(t[4]) for t in allt)), int(sum(float(t[5]) for t in allt))
     else:
         tmax, per_rank = my_ms, None
@@ -524,8 +523,9 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src,
                 "traffic": ncu_traffic(), "launches": int(fused_l), "avg_launch_us": (fused_ms * 1e3 / fused_l) if fused_l else None,
                 "algorithmic_bytes_per_launch": (fused_b / fused_l) if fused_l else None,
-                "share_of_step": (fused_ms / my_ms) if my_ms else None,
-                "preconditioner": {"applies": int(pc_n), "avg_us": (pc_ms * 1e3 / pc_n) if pc_n else None, "share_of_step": (pc_ms / my_ms) if my_ms else None,
+                "share_of_step": (TIMING_EVERY * fused_ms / my_ms) if my_ms else None,
+                "sampling": f"CUDA-event pairs around both kernels of every {TIMING_EVERY}th GMRES solve of the timed region",
+                "preconditioner": {"applies": int(pc_n), "avg_us": (pc_ms * 1e3 / pc_n) if pc_n else None, "share_of_step": (TIMING_EVERY * pc_ms / my_ms) if my_ms else None,
                                    "algorithmic_bytes_per_apply": 3 * 16 * n * n}}
 
     out = {"metric": metric, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -537,8 +537,8 @@ def main():
                "mean_itlinear_per_step": float(np.mean(branch[1:, 3])) if nst > 1 else 0.0,
                "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)},
                "parallelism": ("1 GPU" if world == 1 else
-                               (f"replicas only: {world} independent front branches nu_r = {1.3:g} (1 + 0.002 r), one per GPU, same window each; replicated "
-                                "state; all_gather of rows only" + ("; a rank fell back to nu_0" if nu_fallback else "")) if replicas else
+                               (f"replicas only: {world} independent replicas of the job, one per GPU; replicated state; all_gather of rows only; "
+                                f"max |row difference| between replicas = {replica_dev:g}") if replicas else
                                (f"one window cut into {world} chunks of equal predicted cost; replicated scout inside the timed region "
                                 f"(ds x{SCOUT['ds_factor']:g}, Newton tol {SCOUT['newton_tol']:g}, GMRES reltol {SCOUT['gmres_reltol']:g})")),
                "per_rank": per_rank, "scout_ms": info["scout_ms"], "scout_points": info["scout_points"],

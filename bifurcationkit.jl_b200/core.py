@@ -76,7 +76,7 @@ class Context:
         return {k: getattr(s, k) for k, _ in s._fields_}
 
     def set_timing(self, on):
-        _chk(self, self.lib.bk_set_timing(self.handle, 1 if on else 0))
+        _chk(self, self.lib.bk_set_timing(self.handle, int(on)))  # True / 1: every solve; k > 1: every k-th solve
 
     def sync(self):
         _chk(self, self.lib.bk_sync(self.handle))

@@ -129,7 +129,10 @@ struct bk_ctx {
   double* eig_pinned = nullptr;
   Precond pc;
   bk_stats stats = {};
-  bool timing = false;
+  bool timing = false;      // bk_set_timing: event pairs around the fused kernels / preconditioner applications
+  int timing_every = 1;     // ... of every timing_every-th bk_gmres call only (event records sit between PDL launches: sampling keeps the overhead small)
+  long long solve_count = 0;
+  bool timing_now = false;  // decided per solve
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tpairs;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pc_pairs;  // one pair per preconditioner application (timing enabled)

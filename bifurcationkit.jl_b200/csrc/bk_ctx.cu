@@ -219,6 +219,8 @@ extern "C" int32_t bk_get_stats(bk_ctx* c, bk_stats* out) {
 extern "C" int32_t bk_set_timing(bk_ctx* c, int32_t on) {
   BK_ENTER(c);
   c->timing = on != 0;
+  c->timing_every = on > 1 ? on : 1;  // on = k > 1: time every k-th solve
+  c->timing_now = c->timing && c->timing_every == 1;
   return BK_OK;
 }
 extern "C" int32_t bk_sync(bk_ctx* c) {

@@ -405,7 +405,7 @@ struct TimerScope {
   bk_ctx* c;
   size_t idx;
   bool on;
-  TimerScope(bk_ctx* c_) : c(c_), idx(0), on(c_->timing) {}
+  TimerScope(bk_ctx* c_) : c(c_), idx(0), on(c_->timing_now) {}
   void begin(size_t i) {
     if (!on) return;
     idx = i;
@@ -471,7 +471,7 @@ static int arnoldi_step(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lon
   const long long step_bytes = 8LL * n * (2LL * j + 4) + (op.bordered ? 16LL * n : 0LL);
   c->stats.last_fused_bytes += step_bytes;
   c->stats.last_fused_launches += 2;
-  if (fuse) {
+  if (fuse && (c->timing_now || !c->timing)) {  // with sampled timing the totals cover the timed solves only (bytes and ms must match)
     c->stats.total_fused_bytes += step_bytes;
     c->stats.total_fused_launches += 2;
   }
@@ -514,6 +514,8 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
   c->stats.last_fused_bytes = 0;
   c->stats.last_fused_launches = 0;
   c->stats.last_fused_ms = 0.0;
+  c->solve_count++;
+  c->timing_now = c->timing && (c->solve_count % c->timing_every == 0);
   size_t timer_slot = 0;
 
   BK_CUDA(c, cudaMemsetAsync(x, 0, 8 * (size_t)n, c->stream));  // initially_zero = true (src/LinearSolver.jl:171)
@@ -627,7 +629,7 @@ int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, cons
   }
   BK_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->pc_pairs_used) bk_harvest_pc_timing(c);
-  if (c->timing) {
+  if (c->timing_now) {
     double ms = 0;
     for (size_t i = 0; i < timer_slot && i < c->tpairs.size(); ++i) {
       float t = 0;

@@ -433,7 +433,7 @@ int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) 
   const long long N = c->N;
   bool tail_done = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (c->timing) {  // per-application device time for bench.py's breakdown (event pairs are read back in bk_get_stats)
+  if (c->timing_now) {  // per-application device time for bench.py's breakdown (event pairs are read back in bk_get_stats)
     if (c->pc_pairs_used >= c->pc_pairs.size()) {
       cudaEvent_t a, b;
       cudaEventCreate(&a);

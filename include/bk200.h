@@ -91,7 +91,7 @@ const char* bk_last_error(bk_ctx* ctx);
 int64_t bk_problem_size(bk_ctx* ctx);                       /* N = number of unknowns of F */
 int32_t bk_set_params(bk_ctx* ctx, const double* params, int32_t n);
 int32_t bk_get_stats(bk_ctx* ctx, bk_stats* out);
-int32_t bk_set_timing(bk_ctx* ctx, int32_t on);              /* CUDA-event timing of the fused kernels */
+int32_t bk_set_timing(bk_ctx* ctx, int32_t on);              /* CUDA-event timing of the fused kernels and the preconditioner: 0 off, 1 every bk_gmres call, k > 1 every k-th call (the event records sit between PDL launches; sampling keeps the overhead small) */
 int32_t bk_sync(bk_ctx* ctx);
 void*   bk_stream(bk_ctx* ctx);                              /* cudaStream_t the kernels are launched on */
 

@@ -644,13 +644,14 @@ int32_t bkcpu_sh2d_palc(int32_t nx, int32_t ny, double lx, double ly, double nu,
   return 0;
 }
 
-int32_t bkcpu_max_threads() { return omp_get_max_threads(); }
+// processors available to this process (affinity-aware); NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+int32_t bkcpu_max_threads() { return omp_get_num_procs(); }
 
 // The MGS sweep of GMRES does not scale to every hardware thread of a big host (barrier cost, SMT siblings sharing a core's
 // load ports, NUMA): time one sweep over a 48-vector basis (larger than the caches, like the real solves) for a few thread
 // counts and return the fastest -- "all the host threads it can use" in the sense of the fastest configuration the host offers.
 int32_t bkcpu_calibrate_threads(int64_t n) {
-  const int maxt = omp_get_max_threads();
+  const int maxt = omp_get_num_procs();
   const int nvec = 48;
   int best = maxt;
   double best_t = 1e300;
