@@ -200,6 +200,23 @@ struct Sh2Scratch {
 // central 256 columns (16-byte aligned: x0 is a multiple of 256 and nx is even), issued by the producer lane and counted
 // on `tbar`; the 2 + 2 halo columns of every row are clamped scalar loads by 4 (E + 4) threads.  The stencil is linear in
 // v, so the deferred normalisation in_scale is applied to the results instead of the staged tile.
+// Producer lane: one bulk copy per tile row (central 256 columns), counted on `tbar`.  Issued FIRST, before any L2 prefetch:
+// the tile is on the critical path of the kernel.
+template <int E>
+__device__ __forceinline__ void sh2_tile_issue(const OpDesc& op, const double* __restrict__ in, int x0, int y0, double* scratch,
+                                               unsigned long long* tbar) {
+  using S = Sh2Scratch<E>;
+  const int nx = op.nx, ny = op.ny;
+  const int len = min(BK2_ROW, nx - x0);
+  mbar_arrive_expect_tx(tbar, (unsigned)(len * 8) * (unsigned)S::VY);
+#pragma unroll 1
+  for (int jj = 0; jj < S::VY; ++jj) {
+    int gy = y0 - 2 + jj;
+    gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
+    bulk_g2s(scratch + jj * S::VX + 2, in + x0 + (long long)gy * nx, (unsigned)(len * 8), tbar);
+  }
+}
+
 // RESID: the residual F(v) = -L1 v + l v + nu v^2 - v^3 (examples/SH2d-fronts.jl:31-34) instead of the JVP.
 template <int E, bool BORDERED, bool RESID = false>
 __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __restrict__ in, double in_scale, int x0, int y0,
@@ -210,15 +227,7 @@ __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __
   double* qs = scratch + S::V_ELEMS;
   const int nx = op.nx, ny = op.ny;
   const int len = min(BK2_ROW, nx - x0);
-  if (threadIdx.x == BK2_CONS) {
-    mbar_arrive_expect_tx(tbar, (unsigned)(len * 8) * (unsigned)S::VY);
-#pragma unroll 1
-    for (int jj = 0; jj < S::VY; ++jj) {
-      int gy = y0 - 2 + jj;
-      gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
-      bulk_g2s(vs + jj * S::VX + 2, in + x0 + (long long)gy * nx, (unsigned)(len * 8), tbar);
-    }
-  } else if (threadIdx.x < 4 * S::VY) {
+  if (threadIdx.x < 4 * S::VY) {
     const int jj = threadIdx.x >> 2, h = threadIdx.x & 3;
     const int i = h < 2 ? h : len + h;  // 0, 1, len + 2, len + 3
     int gx = x0 - 2 + i, gy = y0 - 2 + jj;
@@ -296,6 +305,7 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_fused(OpDesc op, con
   bk_pdl_sync();
   const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
   if (threadIdx.x == BK2_CONS) {
+    sh2_tile_issue<E>(op, in, x0, y0, smem2, &tbar);
     // pull what the stencil epilogue and the first ring rounds will read into L2 while the tile is in flight
     const unsigned row_b = (unsigned)(((tl.len + 1) & ~1) * 8);
     for (int r = 0; r < tl.rows; ++r) {
@@ -356,9 +366,12 @@ static __global__ void __launch_bounds__(BK2_THREADS, 4) k2_apply(OpDesc op, con
   const int rows = min(E, op.ny - y0), len = min(BK2_ROW, op.nx - x0);
   __syncthreads();
   const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
-  if (MODE == 0 && threadIdx.x == BK2_CONS) {
-    const unsigned row_b = (unsigned)(len * 8);
-    for (int r = 0; r < rows; ++r) bulk_prefetch_l2(op.u + x0 + (long long)(y0 + r) * op.nx, row_b);
+  if (threadIdx.x == BK2_CONS) {
+    sh2_tile_issue<E>(op, in, x0, y0, smem2, &tbar);
+    if (MODE == 0) {
+      const unsigned row_b = (unsigned)(len * 8);
+      for (int r = 0; r < rows; ++r) bulk_prefetch_l2(op.u + x0 + (long long)(y0 + r) * op.nx, row_b);
+    }
   }
   double val[E];
   double bsum = 0.0;
