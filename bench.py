@@ -120,7 +120,12 @@ def ncu_traffic():
         rows = list(csv.reader(open(p)))
         h = rows[0]
         vals = [float(r[h.index("dram__bytes_read.sum")]) + float(r[h.index("dram__bytes_write.sum")]) for r in rows[2:]]
-        return {"bytes_per_launch": 1e6 * sum(vals) / len(vals), "source": os.path.relpath(p, ROOT) + " (k2_fused, one ncu --set full capture)"}
+        out = {"bytes_per_launch": 1e6 * sum(vals) / len(vals), "source": os.path.relpath(p, ROOT) + " (k2_fused, one ncu --set full capture)"}
+        if p.endswith("r02_ncu_k2_fused.csv"):
+            # the capture sits at Krylov index j = 14 of a 1024^2 solve: algorithmic 8N(j+2) + 16N = 151 MB; moved in addition: the
+            # right-preconditioned input z (its own vector, +8N) and the stencil halo rows ((E+4)/E on z)
+            out.update(j_at_capture=14, algorithmic_bytes_at_capture=8 * 1024 * 1024 * (14 + 2) + 16 * 1024 * 1024)
+        return out
     except Exception:
         return None
 

@@ -471,14 +471,19 @@ static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, dou
   __syncthreads();
   bk_pdl_sync();
   const long long l0 = (long long)blockIdx.x * (2 * C::PP);
-  constexpr int H = C::N / 2;
-  for (int idx = tid; idx < 2 * C::PP * H; idx += C::THREADS) {
-    const int row = idx / H, c2 = idx % H;
-    const long long line = l0 + row;
-    sm[idx] = (line < g.nb) ? __ldg(reinterpret_cast<const double2*>(in + line * g.os) + c2) : make_double2(0.0, 0.0);
+  // the 2 PP input rows (8 N bytes each, 16-byte aligned) arrive by one bulk copy per row on `rbar`; rows beyond the last line are zeroed
+  __shared__ __align__(8) unsigned long long rbar;
+  const int nrows = (int)min((long long)(2 * C::PP), (long long)g.nb - l0);
+  if (tid == 0) {
+    mbar_init(&rbar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&rbar, (unsigned)nrows * (unsigned)(8 * C::N));
+    for (int row = 0; row < nrows; ++row) bulk_g2s(st + row * C::N, in + (l0 + row) * g.os, 8u * C::N, &rbar);
   }
+  for (int idx = nrows * C::N + tid; idx < 2 * C::PP * C::N; idx += C::THREADS) st[idx] = 0.0;
+  __syncthreads();  // rbar initialised (and the zero rows written) before anybody waits / reads
+  mbar_wait(&rbar, 0);
   mbar_wait(&tbar, 0);
-  __syncthreads();
   double2 a[C::E];
   const double* s1 = st + (2 * pr) * C::N;
   const double* s2 = s1 + C::N;
@@ -528,11 +533,12 @@ static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, dou
       o1[C::N + e] = a[i].y;
     }
   }
+  fence_proxy_async_smem();  // the rows were written through the generic proxy: order them before the bulk (async-proxy) reads
   __syncthreads();
-  for (int idx = tid; idx < 2 * C::PP * H; idx += C::THREADS) {
-    const int row = idx / H, c2 = idx % H;
-    const long long line = l0 + row;
-    if (line < g.nb) reinterpret_cast<double2*>(out + line * g.os)[c2] = sm[idx];
+  if (tid == 0) {
+    for (int row = 0; row < nrows; ++row) bulk_s2g(out + (l0 + row) * g.os, st + row * C::N, 8u * C::N);
+    bulk_store_commit();
+    bulk_store_wait_all();  // shared memory must outlive the copies' reads, and the next kernel (PDL) must see the rows
   }
 }
 #endif  // __CUDACC__

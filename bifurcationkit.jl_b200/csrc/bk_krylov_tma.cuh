@@ -249,11 +249,20 @@ __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __
   __syncthreads();
   const int t = threadIdx.x;
   const double l = op.par[0], nu = op.par[1];
+  const int gx = x0 + t;
+  const bool colok = t < BK2_ROW && gx < nx;
+  const int rows = min(E, ny - y0);
+  // Epilogue in sub-passes so that each issues E independent global loads before the first use (the first version mixed the
+  // loads of u, a, b with the arithmetic row by row: long-scoreboard stalls 11.7 per issue at 54 registers, ncu round 2).
+  double g[E];
+  if (!RESID) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) g[e] = (colok && e < rows) ? __ldg(op.u + gx + (long long)(y0 + e) * nx) : 0.0;
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    const int gx = x0 + t, gy = y0 + e;
     double r = 0.0;
-    if (t < BK2_ROW && gx < nx && gy < ny) {
+    if (colok && e < rows) {
       const double* p = qs + (t + 1) + (e + 1) * S::QX;
       const double c0 = p[0];
       const double l1v = in_scale * (c0 + op.cx * (p[-1] - 2.0 * c0 + p[1]) + op.cy * (p[-S::QX] - 2.0 * c0 + p[S::QX]));
@@ -261,17 +270,23 @@ __device__ __forceinline__ void sh2_tile_eval(const OpDesc& op, const double* __
       if (RESID) {
         r = v * (l + v * (nu - v)) - l1v;
       } else {
-        const double uu = __ldg(op.u + gx + (long long)gy * nx);
-        const double coef = l + uu * (2.0 * nu - 3.0 * uu);
+        const double coef = l + g[e] * (2.0 * nu - 3.0 * g[e]);
         r = op.a0 * v + op.a1 * (coef * v - l1v);
-      }
-      if (BORDERED) {
-        const long long gi = gx + (long long)gy * nx;
-        r += xp * __ldg(op.ba + gi) + op.bshift * v;
-        *bsum = fma(__ldg(op.bb + gi), v, *bsum);
+        if (BORDERED) r += op.bshift * v;
       }
     }
     val[e] = r;
+  }
+  if (BORDERED) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) g[e] = (colok && e < rows) ? __ldg(op.ba + gx + (long long)(y0 + e) * nx) : 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) val[e] = fma(xp, g[e], val[e]);
+#pragma unroll
+    for (int e = 0; e < E; ++e) g[e] = (colok && e < rows) ? __ldg(op.bb + gx + (long long)(y0 + e) * nx) : 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (colok && e < rows) *bsum = fma(g[e], in_scale * vs[(t + 2) + (e + 2) * S::VX], *bsum);
   }
 }
 
