@@ -503,16 +503,20 @@ def main():
         rows_h, ms_h, d_h, info_h = window_job(bk, ctx, ls, n, uh, s_total, rank, jw, torch, flush, timing=False, wrap=ctx.pinned_array, nsteps=K * B)
         ctx.pin_host = False
         bk.palc.V.host_alloc = None
-        th = torch.tensor([ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"])], dtype=torch.float64, device=f"cuda:{dev}")
+        th = torch.tensor([ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"]), float(info_h["work_newton"]), float(info_h["work_linear"]),
+                           float(info_h["rejected"])], dtype=torch.float64, device=f"cuda:{dev}")
         if dist:
             allh = [torch.zeros_like(th) for _ in range(world)]
             dist.all_gather(allh, th)
             tmax_h = max(float(t[0]) for t in allh)
             h2d, d2h = sum(float(t[1]) for t in allh), sum(float(t[2]) for t in allh)
+            wh = [int(sum(float(t[k]) for t in allh)) for k in (3, 4, 5)]
         else:
             tmax_h, h2d, d2h = ms_h, float(d_h["h2d_bytes"]), float(d_h["d2h_bytes"])
+            wh = [info_h["work_newton"], info_h["work_linear"], info_h["rejected"]]
         e2e = {"value": (world if replicas else 1) * K * B / (tmax_h * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
-               "note": "the same window with pinned host NumPy state vectors: every residual / Jacobian / bordered solve crosses the C ABI with host pointers (H2D + D2H inside the timed region); bytes are per bench step (batch), all ranks"}
+               "corrector_work": {"newton_its": int(wh[0]), "linear_its": int(wh[1]), "rejected_steps": int(wh[2])},
+               "note": "step acceptance in the snaking region is sensitive to rounding: the host-vector path (BLAS reductions) rejects a different set of steps than the device path, so its corrector work -- and its steps/s -- differ from run to run by up to 1.5x; the same window with pinned host NumPy state vectors: every residual / Jacobian / bordered solve crosses the C ABI with host pointers (H2D + D2H inside the timed region); bytes are per bench step (batch), all ranks"}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -540,7 +544,7 @@ def main():
            "details": dict({
                "continuation_steps_taken": int(nst - (world if replicas else (1 if world == 1 else 0))), "mean_itnewton": float(np.mean(branch[1:, 2])) if nst > 1 else 0.0,
                "mean_itlinear_per_step": float(np.mean(branch[1:, 3])) if nst > 1 else 0.0,
-               "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)},
+               "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)}, "rejected_steps": int(sum(p["rejected"] for p in per_rank)) if per_rank else int(info["rejected"]),
                "parallelism": ("1 GPU" if world == 1 else
                                (f"replicas only: {world} independent replicas of the job, one per GPU; replicated state; all_gather of rows only; "
                                 f"max |row difference| between replicas = {replica_dev:g}") if replicas else
