@@ -48,7 +48,7 @@ enum {
   BK_PC_SH_DCT = 1,     /* (L1 + shift I)^-1 by separable DCT-II (exact for the Neumann-closure operator) */
   BK_PC_CHAN_TRIDIAG = 2, /* lu(P), P = tridiagonal Laplacian with identity boundary rows (chan.jl:108-109) */
   BK_PC_CGL_DST = 3,    /* per-component (a0 I + a1 Lap_dirichlet)^-1 by DST-I (block Jacobi over slices) */
-  BK_PC_POTRAP_CIRC = 4 /* Trapeze PO Jacobian of cGL linearised at the trivial state: DST-I in space (dense, cuBLAS DGEMM),
+  BK_PC_POTRAP_CIRC = 4 /* Trapeze PO Jacobian of cGL linearised at the trivial state: DST-I in space (mixed-radix FFT of the odd extension, bk_fft_gen.cuh),
                            u1 +- i u2, DFT over the M-1 cyclic slices, scalar symbol; a0 = period T.  Stand-in for the ILU
                            of the assembled PO Jacobian (examples/cGL2d.jl:209-213) */
 };
@@ -160,9 +160,9 @@ int32_t bk_potrap_set_section(bk_ctx* ctx, const double* phi, const double* xpi)
 /* ---- environment switches read once by the library (tuning / diagnostics; none is needed for normal use)
  *   BK2_E=1..8          tile height of the TMA-ring Arnoldi kernels instead of the heuristic (bk_krylov.cu::plan2)
  *   BK_NO_PDL=1         launch without programmatic dependent launch (plain stream order)
- *   BK_DCT_W, BK_DCT_THREADS   lines per CTA / threads per CTA of the DCT kernels
- *   BK_DCT_V2=1         second version of the DCT kernels (bk_dct2.cuh) -- opt-in until it has been validated on a GPU
- *   BK_CGL_DST_GEMM=1   BK_PC_CGL_DST through cuBLAS GEMMs instead of the dense-line kernel -- opt-in, same status */
+ *   BK_FFT_LOGE=2..5    complex values per thread (2^e) of the power-of-two transform kernels instead of the per-size default
+ *   BK_FFT_NO_FAST=1    every transform through the general mixed-radix kernel (bk_fft_gen.cuh)
+ *   BK_SH2D_NO_TMA=1    stand-alone SH2d residual / JVP on the first-generation 64 x 32 tile kernel instead of the TMA-staged tile */
 
 #ifdef __cplusplus
 }
