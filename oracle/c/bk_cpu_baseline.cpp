@@ -56,6 +56,19 @@ struct PVec {
     p = q;
     n = m;
   }
+  // rows x len array whose row slices are first-touched by the thread that will work on them (the Krylov basis: every BLAS-1
+  // loop runs over ONE row with a static schedule, so slice t of every row must live on thread t's NUMA node; a flat parallel
+  // first touch would put whole rows on single nodes)
+  void resize_rows(size_t rows, size_t len) {
+    free(p);
+    n = rows * len;
+    p = n ? (T*)aligned_alloc(64, ((n * sizeof(T) + 63) / 64) * 64) : nullptr;
+    for (size_t r = 0; r < rows; ++r) {
+      T* q = p + r * len;
+#pragma omp parallel for schedule(static)
+      for (long i = 0; i < (long)len; ++i) q[i] = T();
+    }
+  }
   void assign(size_t m, T v) {
     resize(m);
 #pragma omp parallel for schedule(static)
@@ -365,7 +378,7 @@ struct GmresOpts {
 int gmres(const LinOp& A, const double* b, double* x, const GmresOpts& o, bool* converged, vec& V, vec& w, vec& z) {
   const long n = A.n();
   const int restart = (int)std::min<long>(o.restart, n);
-  if ((long)V.size() < (long)(restart + 1) * n) V.resize((size_t)(restart + 1) * n);
+  if ((long)V.size() < (long)(restart + 1) * n) V.resize_rows((size_t)(restart + 1), (size_t)n);
   if ((long)w.size() < n) w.resize(n);
   if ((long)z.size() < n) z.resize(n);
   std::vector<double> H((size_t)(restart + 1) * restart, 0.0), g(restart + 1), cs(restart), sn(restart), y(restart);
@@ -658,8 +671,9 @@ int32_t bkcpu_calibrate_threads(int64_t n) {
   for (int t : {8, 16, 32, 48, 64, 96, 128, 192, 256}) {
     if (t > maxt) t = maxt;
     omp_set_num_threads(t);
-    vec Vb((size_t)n * nvec), w((size_t)n);   // first-touched by THIS team
-    Vb.assign((size_t)n * nvec, 1e-3);
+    vec Vb, w((size_t)n);   // first-touched by THIS team, row by row like the solver's basis
+    Vb.resize_rows(nvec, (size_t)n);
+    for (int i = 0; i < nvec; ++i) scal_copy(Vb.data() + (size_t)i * n, 0.0, Vb.data() + (size_t)i * n, n);
     w.assign((size_t)n, 1.0);
     for (int rep = 0; rep < 2; ++rep) {
       const auto t0 = std::chrono::steady_clock::now();

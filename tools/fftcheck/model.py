@@ -243,6 +243,41 @@ def bank_report(pl, pad, pairs_interleaved=1):
     return res
 
 
+def bank_report_em(pl, pad, PP, nthreads=None):
+    """Wavefronts per ideal wavefront of every pass (and of the partner read, last entry) for the layout the kernels use:
+    thread tid = tau * PP + pr, slot(pos, pr) = pad(pos) * PP + pr  (element-major, pairs interleaved)."""
+    n, E, T = pl.n, pl.E, pl.T
+    nthreads = nthreads or min(T * PP, 256)
+    lanes = [(tid // PP, tid % PP) for tid in range(nthreads)]
+    slot = lambda pr, i: pad(i) * PP + pr
+    res = []
+    for p, r in enumerate(pl.rad):
+        tot = ideal = 0
+        for w0 in range(0, len(lanes), 32):
+            warp = lanes[w0:w0 + 32]
+            for u in range(E // r):
+                for a in range(r):
+                    sl = [slot(pr, pl.positions(p, tau, u)[0][a]) for tau, pr in warp]
+                    tot += wavefronts(sl)
+                    ideal += (len(sl) + 7) // 8
+        res.append(tot / ideal)
+    tot = ideal = 0
+    rl = pl.rad[-1]
+    for w0 in range(0, len(lanes), 32):
+        warp = lanes[w0:w0 + 32]
+        for u in range(E // rl):
+            for j in range(rl):
+                sl = []
+                for tau, pr in warp:
+                    pp = pl.positions(len(pl.rad) - 1, tau, u)[0][brev(j, rl)]
+                    k = pl.k_of_pos[pp]
+                    sl.append(slot(pr, pl.pos_of_k[(n - k) % n]))
+                tot += wavefronts(sl)
+                ideal += (len(sl) + 7) // 8
+    res.append(tot / ideal)
+    return res
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(0)
     for n in (64, 128, 256, 512, 1024, 2048):
