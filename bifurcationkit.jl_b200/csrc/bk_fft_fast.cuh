@@ -43,7 +43,15 @@ struct Cfg {
   // resident threads per SM the register budget is sized for (launch bounds): few fat threads (E = 32: 255 registers) ... many thin ones
   static constexpr int TPSM = LOGE == 5 ? 256 : LOGE == 4 ? 512 : LOGE == 3 ? 768 : 1024;
   static constexpr int MINB = TPSM / THREADS > 0 ? TPSM / THREADS : 1;
-  static constexpr int SLOTS = pad(N - 1) + 1;                     // padded complex slots per pair
+  // padding of the NATURAL-order staging array of the contiguous kernels (scatter by register = digit-reversed k, then read
+  // k = tau + T i): conflict-free choices from the same bank model (tools/fftcheck/padsearch.py)
+  static constexpr int NB = LOGE == 2 ? (LOGN <= 6 ? 0 : LOGN <= 8 ? 4 : LOGN <= 10 ? 6 : 8)
+                          : LOGE == 3 ? (LOGN <= 6 ? 0 : LOGN <= 9 ? 3 : 6)
+                          : LOGE == 4 ? (LOGN <= 8 ? 0 : 4)
+                                      : (LOGN <= 10 ? 0 : 5);
+  __host__ __device__ static constexpr int padn(int k) { return k + (k >> 2) + (NB ? (k >> NB) : 0); }
+  static constexpr int SLOTS_POS = pad(N - 1) + 1, SLOTS_NAT = padn(N - 1) + 1;
+  static constexpr int SLOTS = SLOTS_POS > SLOTS_NAT ? SLOTS_POS : SLOTS_NAT;   // padded complex slots per pair
   static constexpr size_t SMEM_DATA = sizeof(double2) * (size_t)SLOTS * PP;
   __host__ __device__ static constexpr int logr(int p) { return p < F ? LOGE : RB; }
   __host__ __device__ static constexpr int logNp(int p) { return LOGN - LOGE * p; }       // block length before pass p
@@ -458,42 +466,38 @@ static __global__ void BKF_BOUNDS(C) k_strided(const double* __restrict__ in, do
 }
 
 // ------------------------------------------------------------------------------------------------ contiguous lines (x)
-// MODE 0: forward, 1: inverse.  A CTA owns 2 PP consecutive lines; rows are staged in shared memory with coalesced 16-byte
-// accesses (the staging area aliases the FFT work array).
+// MODE 0: forward, 1: inverse.  A CTA owns 2 PP consecutive lines (PP pairs).  The Makhoul side (x[2m], x[2n-1-2m]) is read /
+// written straight from / to global memory (8-byte accesses at a 16-byte stride: the other half of every sector belongs to the
+// mirror register of another thread of the same CTA, L1 / L2 merge them); the frequency side goes through a NATURAL-order
+// shared-memory array with its own conflict-free padding, so that global accesses in k are fully coalesced.  (The first
+// version staged whole rows in natural order and scattered into them by digit-reversed k: 54-71 % of its shared-memory
+// wavefronts were bank conflicts, profiles/r02_ncu_fft.csv.)
+template <class C>
+__device__ __forceinline__ int nslot(int k, int pr) { return C::padn(k) * C::PP + pr; }
+
 template <class C, int MODE>
 static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, double* __restrict__ out, Geom g, Tables tbg) {
   extern __shared__ __align__(128) double2 sm_fast[];
   __shared__ __align__(8) unsigned long long tbar;
   double2* sm = sm_fast;
-  double* st = reinterpret_cast<double*>(sm_fast);  // st[row * N + e]
   const Tables tb = stage_tables<C, false>(tbg, sm, &tbar);
   const int tid = threadIdx.x, pr = tid % C::PP, tau = tid / C::PP;
   __syncthreads();
   bk_pdl_sync();
-  const long long l0 = (long long)blockIdx.x * (2 * C::PP);
-  // the 2 PP input rows (8 N bytes each, 16-byte aligned) arrive by one bulk copy per row on `rbar`; rows beyond the last line are zeroed
-  __shared__ __align__(8) unsigned long long rbar;
-  const int nrows = (int)min((long long)(2 * C::PP), (long long)g.nb - l0);
-  if (tid == 0) {
-    mbar_init(&rbar, 1);
-    fence_mbar_init();
-    mbar_arrive_expect_tx(&rbar, (unsigned)nrows * (unsigned)(8 * C::N));
-    for (int row = 0; row < nrows; ++row) bulk_g2s(st + row * C::N, in + (l0 + row) * g.os, 8u * C::N, &rbar);
-  }
-  for (int idx = nrows * C::N + tid; idx < 2 * C::PP * C::N; idx += C::THREADS) st[idx] = 0.0;
-  __syncthreads();  // rbar initialised (and the zero rows written) before anybody waits / reads
-  mbar_wait(&rbar, 0);
-  mbar_wait(&tbar, 0);
+  const long long lineA = ((long long)blockIdx.x * C::PP + pr) * 2, lineB = lineA + 1;
+  const bool vA = lineA < g.nb, vB = lineB < g.nb;
+  const double* inA = in + lineA * g.os;
+  const double* inB = in + lineB * g.os;
+  double* outA = out + lineA * g.os;
+  double* outB = out + lineB * g.os;
   double2 a[C::E];
-  const double* s1 = st + (2 * pr) * C::N;
-  const double* s2 = s1 + C::N;
   if (MODE == 0) {
 #pragma unroll
     for (int i = 0; i < C::E; ++i) {
       const int e = row_of<C>(i, tau);
-      a[i] = make_double2(s1[e], s2[e]);
+      a[i] = make_double2(vA ? __ldg(inA + e) : 0.0, vB ? __ldg(inB + e) : 0.0);
     }
-    __syncthreads();
+    mbar_wait(&tbar, 0);
     fwd_passes<C, 0>(a, sm, tb, tau, pr);
     park<C>(a, sm, tau, pr);
     __syncthreads();
@@ -503,42 +507,45 @@ static __global__ void BKF_BOUNDS(C) k_contig(const double* __restrict__ in, dou
       const double2 z = a[reg], zp = partner<C>(sm, reg_pos<C>(tau, reg), pr, k);
       const double2 w = tb.om[reg * C::T + tau];
       const double sx = z.x + zp.x, sy_ = z.y - zp.y, dx = z.x - zp.x, dy = z.y + zp.y;
-      a[reg] = make_double2(fma(w.x, sx, -(w.y * sy_)), fma(w.x, dy, w.y * dx));
+      a[reg] = make_double2(fma(w.x, sx, -(w.y * sy_)), fma(w.x, dy, w.y * dx));   // (2 C1[k], 2 C2[k])
     }
-    __syncthreads();
-    double* o1 = st + (2 * pr) * C::N;
+    __syncthreads();  // every partner read is done: the natural-order array may overwrite the work array
 #pragma unroll
-    for (int reg = 0; reg < C::E; ++reg) {
-      const int k = k_of_pos<C>(reg_pos<C>(tau, reg));
-      o1[k] = a[reg].x;
-      o1[C::N + k] = a[reg].y;
+    for (int reg = 0; reg < C::E; ++reg) sm[nslot<C>(k_of_pos<C>(reg_pos<C>(tau, reg)), pr)] = a[reg];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < C::E; ++i) {
+      const int k = i * C::T + tau;
+      const double2 d = sm[nslot<C>(k, pr)];
+      if (vA) outA[k] = d.x;
+      if (vB) outB[k] = d.y;
     }
   } else {
+#pragma unroll
+    for (int i = 0; i < C::E; ++i) {
+      const int k = i * C::T + tau;
+      sm[nslot<C>(k, pr)] = make_double2(vA ? __ldg(inA + k) : 0.0, vB ? __ldg(inB + k) : 0.0);
+    }
+    mbar_wait(&tbar, 0);
+    __syncthreads();
+    // Zhat[k] = conj(w_k) ((D[k].x + D[n-k].y) + i (D[k].y - D[n-k].x)),  D[k] = C1[k] + i C2[k],  D[n] = 0
 #pragma unroll
     for (int reg = 0; reg < C::E; ++reg) {
       const int k = k_of_pos<C>(reg_pos<C>(tau, reg)), nk = (C::N - k) & (C::N - 1);
       const double2 w = tb.om[reg * C::T + tau];
-      const double d1 = s1[k], d2 = s2[k];
-      const double n1 = k ? s1[nk] : 0.0, n2 = k ? s2[nk] : 0.0;
-      a[reg] = cmulc(make_double2(d1 + n2, d2 - n1), w);
+      const double2 d = sm[nslot<C>(k, pr)];
+      double2 dn = sm[nslot<C>(nk, pr)];
+      if (k == 0) dn = make_double2(0.0, 0.0);
+      a[reg] = cmulc(make_double2(d.x + dn.y, d.y - dn.x), w);
     }
-    __syncthreads();
+    __syncthreads();  // the natural-order array is dead: the inverse passes reuse the memory
     inv_passes<C, C::NP - 1>(a, sm, tb, tau, pr);
-    __syncthreads();
-    double* o1 = st + (2 * pr) * C::N;
 #pragma unroll
     for (int i = 0; i < C::E; ++i) {
       const int e = row_of<C>(i, tau);
-      o1[e] = a[i].x;
-      o1[C::N + e] = a[i].y;
+      if (vA) outA[e] = a[i].x;
+      if (vB) outB[e] = a[i].y;
     }
-  }
-  fence_proxy_async_smem();  // the rows were written through the generic proxy: order them before the bulk (async-proxy) reads
-  __syncthreads();
-  if (tid == 0) {
-    for (int row = 0; row < nrows; ++row) bulk_s2g(out + (l0 + row) * g.os, st + row * C::N, 8u * C::N);
-    bulk_store_commit();
-    bulk_store_wait_all();  // shared memory must outlive the copies' reads, and the next kernel (PDL) must see the rows
   }
 }
 #endif  // __CUDACC__
