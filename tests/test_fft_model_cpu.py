@@ -40,3 +40,25 @@ def test_shipped_padding_is_conflict_free_in_the_bank_model():
         ratios = model.bank_report_em(pl, pad, PP)
         assert max(ratios[:-1]) <= 1.0 + 1e-9, (n, E, ratios)   # every FFT pass: one wavefront per 128 bytes
         assert ratios[-1] <= 1.15, (n, E, ratios)                # the partner read Z[n-k]: at most 15 % extra wavefronts
+
+
+def test_natural_order_staging_padding_is_conflict_free():
+    """padn(k) = k + k/4 (+ k/2^NB) with the NB table of csrc/bk_fft_fast.cuh::Cfg: the digit-reversed scatter and the natural
+    read of the contiguous kernels' staging array are both conflict-free in the bank model"""
+    def nb(loge, logn):
+        if loge == 2:
+            return 0 if logn <= 6 else 4 if logn <= 8 else 6 if logn <= 10 else 8
+        if loge == 3:
+            return 0 if logn <= 6 else 3 if logn <= 9 else 6
+        if loge == 4:
+            return 0 if logn <= 8 else 4
+        return 0 if logn <= 10 else 5
+    for loge in (2, 3, 4, 5):
+        for logn in range(max(6, loge + 1), 12):
+            n, E = 1 << logn, 1 << loge
+            pl = model.Plan(n, E)
+            b = nb(loge, logn)
+            padn = (lambda k, b=b: k + (k >> 2) + ((k >> b) if b else 0))
+            PP = max(2, 64 // (n // E))
+            w, r = model.bank_report_natural(pl, padn, PP)
+            assert w <= 1.0 + 1e-9 and r <= 1.0 + 1e-9, (n, E, b, w, r)

@@ -278,6 +278,32 @@ def bank_report_em(pl, pad, PP, nthreads=None):
     return res
 
 
+def bank_report_natural(pl, padn, PP, nthreads=None):
+    """Contiguous kernels: (scatter of the registers into the natural-order array nat[padn(k) * PP + pr], read k = tau + T i):
+    wavefronts per ideal wavefront of both accesses."""
+    n, E, T = pl.n, pl.E, pl.T
+    nthreads = nthreads or min(T * PP, 256)
+    lanes = [(tid // PP, tid % PP) for tid in range(nthreads)]
+    rl, P = pl.rad[-1], len(pl.rad) - 1
+    tot = ideal = 0
+    for w0 in range(0, len(lanes), 32):
+        warp = lanes[w0:w0 + 32]
+        for u in range(E // rl):
+            for j in range(rl):
+                sl = [padn(pl.k_of_pos[pl.positions(P, tau, u)[0][brev(j, rl)]]) * PP + pr for tau, pr in warp]
+                tot += wavefronts(sl)
+                ideal += (len(sl) + 7) // 8
+    w = tot / ideal
+    tot = ideal = 0
+    for w0 in range(0, len(lanes), 32):
+        warp = lanes[w0:w0 + 32]
+        for i in range(E):
+            sl = [padn(i * T + tau) * PP + pr for tau, pr in warp]
+            tot += wavefronts(sl)
+            ideal += (len(sl) + 7) // 8
+    return w, tot / ideal
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(0)
     for n in (64, 128, 256, 512, 1024, 2048):
