@@ -37,8 +37,10 @@ def _chk(ctx, status):
 class Context:
     """One per GPU: owns the CUDA stream, Krylov workspace and the problem description."""
 
-    def __init__(self, kind, dims, lengths=(1.0, 1.0, 1.0), krylov_m=100, device=0, params=None):
+    def __init__(self, kind, dims, lengths=(1.0, 1.0, 1.0), krylov_m=100, device=0, params=None, complex=False):
         self.lib = _l.load()
+        if complex:
+            kind |= _l.BK_COMPLEX  # vectors [re; im] of length 2 N0, shifts a0 + i a0_imag (include/bk200.h)
         d = (C.c_int64 * 3)(*(list(dims) + [1, 1, 1])[:3])
         L = (C.c_double * 3)(*(list(lengths) + [1.0, 1.0, 1.0])[:3])
         h = C.c_void_p()
@@ -49,6 +51,8 @@ class Context:
             raise _l.BK200Error(f"bk_ctx_create failed ({st}): {msg.decode()}")
         self.kind, self.dims, self.lengths, self.krylov_m = kind, tuple(dims), tuple(lengths), krylov_m
         self.N = int(self.lib.bk_problem_size(h))
+        self.N0 = int(self.lib.bk_state_size(h))
+        self.complex = bool(complex)
         self.params = None
         if params is not None:
             self.set_params(params)
@@ -130,6 +134,18 @@ class Context:
         """J = jacobian(prob, u, params): snapshot of (u, current params) inside the context."""
         _chk(self, self.lib.bk_jac_set_state(self.handle, _l.ptr(u)))
         return Jacobian(self)
+
+    def cjacobian(self, u, transpose=False):
+        """BK_COMPLEX contexts: J (or J') at the real state u, acting on complex vectors."""
+        assert self.complex
+        _chk(self, self.lib.bk_jac_set_state(self.handle, _l.ptr(u)))
+        return ComplexJacobian(self, transpose)
+
+    def set_shift_imag(self, a0_imag):
+        _chk(self, self.lib.bk_jac_set_shift_imag(self.handle, float(a0_imag)))
+
+    def set_transpose(self, on):
+        _chk(self, self.lib.bk_jac_set_transpose(self.handle, 1 if on else 0))
 
     def jvp(self, v, out=None, a0=0.0, a1=1.0):
         out = self._like(v) if out is None else out
@@ -226,6 +242,30 @@ class Jacobian:
         return self.ctx.jvp(dx)
 
 
+def csplit(z):
+    """complex array -> the split layout [re; im] of a BK_COMPLEX context"""
+    z = np.asarray(z)
+    return np.ascontiguousarray(np.concatenate([z.real, z.imag]), dtype=np.float64)
+
+
+def cjoin(x):
+    n = len(x) // 2
+    return x[:n] + 1j * x[n:]
+
+
+class ComplexJacobian:
+    """J or its transpose (apply_jacobian(prob, x, par, dx, true), src/codim2/MinAugHopf.jl:152-155) on complex NumPy vectors;
+    handle on a BK_COMPLEX context's linearisation state, like `Jacobian`."""
+
+    def __init__(self, ctx, transpose=False):
+        self.ctx, self.transpose = ctx, bool(transpose)
+
+    def __call__(self, z):
+        self.ctx.set_transpose(self.transpose)
+        self.ctx.set_shift_imag(0.0)
+        return cjoin(self.ctx.jvp(csplit(z)))
+
+
 def make_opts(reltol=1e-8, abstol=0.0, restart=200, maxiter=100, pc_side=_l.BK_SIDE_NONE, orth=_l.BK_ORTH_CGS, fused=True):
     return _l.GmresOpts(reltol, abstol, restart, maxiter, pc_side, orth, int(fused), 0)  # fused: 0 off, 1 auto, 2 force
 
@@ -261,6 +301,23 @@ class GMRESB200:
         _chk(ctx, ctx.lib.bk_gmres(ctx.handle, _l.ptr(rhs), _l.ptr(x), a0, a1, C.byref(o), C.byref(cv), C.byref(it), C.byref(rn)))
         self.last_resnorm = rn.value
         return x, bool(cv.value), it.value
+
+
+class ComplexGMRESB200(GMRESB200):
+    """ls(J, rhs; a0 = complex shift, a1) on a BK_COMPLEX context: (a0 I + a1 J) x = rhs for complex rhs -- the
+    `shift = Complex(0, -omega)` solves of the Hopf functional (src/codim2/MinAugHopf.jl:19-40).  GMRES runs on the
+    real-equivalent system; the solution, not the iterate sequence, is what parity pins."""
+
+    def __call__(self, J, rhs, a0=0.0, a1=1.0):
+        ctx = J.ctx
+        a0 = complex(a0)
+        ctx.set_transpose(getattr(J, "transpose", False))
+        ctx.set_shift_imag(a0.imag)
+        try:
+            x, cv, it = GMRESB200.__call__(self, J, csplit(rhs), a0=a0.real, a1=a1)
+        finally:
+            ctx.set_shift_imag(0.0)
+        return cjoin(x), cv, it
 
 
 class BorderingBLSB200:

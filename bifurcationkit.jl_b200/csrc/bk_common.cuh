@@ -36,6 +36,10 @@ struct OpDesc {
   // potrap extras
   const double* phi;     // section (length N-1)
   const double* fcache;  // F(x_i) cache, M slices (device)
+  // complexified contexts (BK_COMPLEX): N = 2 N0, vectors are [re; im], operator ((a0 + i a0i) I + a1 J) with J real
+  int cplx;
+  double a0i;
+  int transpose;         // J' instead of J (cGL2d: transposed reaction block; SH: self-adjoint)
 };
 
 // general-length transform plan (bk_fft_gen.cuh), passed by value to the kernels
@@ -83,7 +87,11 @@ struct bk_ctx {
   long long dims[3] = {1, 1, 1};
   double lengths[3] = {1, 1, 1};
   double par[BK_MAX_PAR] = {0};
-  long long N = 0;        // unknowns
+  long long N = 0;        // unknowns (BK_COMPLEX: 2 N0)
+  long long N0 = 0;       // size of the real problem: length of the state u and of F(u)
+  bool cplx = false;      // BK_COMPLEX context
+  double shift_imag = 0;  // imaginary part of a0 (bk_jac_set_shift_imag)
+  bool transpose = false; // bk_jac_set_transpose
   int m = 0;              // Krylov dimension capacity (basis holds m+1 vectors of length N+1)
   long long ld = 0;       // leading dimension of the basis (>= N+1, multiple of 32)
   // Jacobian state

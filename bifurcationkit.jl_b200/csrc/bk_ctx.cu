@@ -67,6 +67,8 @@ extern "C" int32_t bk_ctx_create(int32_t device, int32_t kind, const int64_t dim
   if (!c) return BK_ERR_ARG;
   *out = c;  // returned even on failure so the caller can read bk_last_error
   c->device = device;
+  c->cplx = (kind & BK_COMPLEX) != 0;
+  kind &= ~BK_COMPLEX;
   c->kind = kind;
   for (int i = 0; i < 3; ++i) {
     c->dims[i] = dims ? (dims[i] > 0 ? dims[i] : 1) : 1;
@@ -83,6 +85,9 @@ extern "C" int32_t bk_ctx_create(int32_t device, int32_t kind, const int64_t dim
   }
   BK_CHECK(c, n >= 2, "problem too small");
   BK_CHECK(c, krylov_m >= 1 && krylov_m <= 1024, "krylov_m out of range");
+  BK_CHECK(c, !(c->cplx && kind == BK_POTRAP_CGL2D), "BK_COMPLEX is not available for the periodic-orbit functional");
+  c->N0 = n;
+  if (c->cplx) n *= 2;  // [re; im]
   c->N = n;
   c->m = krylov_m;
   c->ld = ((n + 2 + 31) / 32) * 32;  // >= N + 2: bordered vectors (N+1) keep one zero pad element for even-sized TMA rows
@@ -188,6 +193,7 @@ extern "C" int32_t bk_ctx_destroy(bk_ctx* c) {
 
 extern "C" const char* bk_last_error(bk_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" int64_t bk_problem_size(bk_ctx* c) { return c ? c->N : 0; }
+extern "C" int64_t bk_state_size(bk_ctx* c) { return c ? c->N0 : 0; }
 extern "C" int32_t bk_set_params(bk_ctx* c, const double* p, int32_t n) {
   BK_ENTER(c);
   BK_CHECK(c, p && n >= 0 && n <= BK_MAX_PAR, "bad params");

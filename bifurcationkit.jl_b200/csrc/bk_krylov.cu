@@ -327,6 +327,7 @@ static inline int chunk_grid(long long n) { return (int)((n + BK_TILE - 1) / BK_
 // 3-D: the fused kernel is still the first-generation one (64 KB tiles, 2.3 waves at 128^3) and measured 17% slower per
 // iteration than stand-alone JVP + TMA-ring dots, so "automatic" keeps it off until a TMA-ring 3-D kernel exists.
 static bool fused_available(const OpDesc& op, int fused_mode = 2) {
+  if (op.cplx) return false;  // the fused kernels tile one real grid; a split complex vector takes the two-launch path
   if (op.kind == BK_SH2D) return !op.bordered || (op.nx % 2 == 0);
   if (op.kind == BK_SH3D) return !op.bordered && fused_mode >= 2;
   return false;

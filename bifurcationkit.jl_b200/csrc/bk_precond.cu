@@ -361,7 +361,7 @@ extern "C" int32_t bk_precond_setup(bk_ctx* c, int32_t kind, double a0, double a
     pc.po_nu = c->par[2];
   } else if (kind == BK_PC_CHAN_TRIDIAG) {
     BK_CHECK(c, c->kind == BK_CHAN, "BK_PC_CHAN_TRIDIAG needs a chan context");
-    long long n = c->N;
+    long long n = c->N0;
     double s = (double)(n - 1) * (double)(n - 1);
     std::vector<double> lo(n, s), di(n, -2 * s), up(n, s), tri(3 * n);
     di[0] = 1;
@@ -426,11 +426,21 @@ static int transform_pass(bk_ctx* c, int d, int mode, const double* in, double* 
 
 static inline bool aligned16(const void* a, const void* b) { return ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0; }
 
+static int precond_apply_one(bk_ctx* c, const double* in, double* out, long long n);
+
 int bk_precond_apply_dev(bk_ctx* c, const double* in, double* out, long long n) {
-  Precond& pc = c->pc;
-  BK_CHECK(c, pc.kind != BK_PC_NONE, "no preconditioner set up (bk_precond_setup)");
+  BK_CHECK(c, c->pc.kind != BK_PC_NONE, "no preconditioner set up (bk_precond_setup)");
   BK_CHECK(c, in != out, "preconditioner: in-place application is not supported");
-  const long long N = c->N;
+  if (!c->cplx) return precond_apply_one(c, in, out, n);
+  // split complex vector: the real preconditioner on both halves (border entries, if any, follow the second half)
+  BK_CHECK(c, n >= c->N, "preconditioner: vector shorter than the complexified problem");
+  BK_TRY(precond_apply_one(c, in, out, c->N0));
+  return precond_apply_one(c, in + c->N0, out + c->N0, n - c->N0);
+}
+
+static int precond_apply_one(bk_ctx* c, const double* in, double* out, long long n) {
+  Precond& pc = c->pc;
+  const long long N = c->N0;
   bool tail_done = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (c->timing_now) {  // per-application device time for bench.py's breakdown (event pairs are read back in bk_get_stats)

@@ -61,6 +61,7 @@ __device__ __forceinline__ void cgl_nl(const CglPar& p, double u1, double u2, do
   f1 = p.r * u1 - p.nu * u2 - ua * (p.c3 * u1 - p.mu * u2) - p.c5 * ua * ua * u1;
   f2 = p.r * u2 + p.nu * u1 - ua * (p.c3 * u2 + p.mu * u1) - p.c5 * ua * ua * u2;
 }
+template <bool TR = false>
 __device__ __forceinline__ void cgl_dnl(const CglPar& p, double u1, double u2, double d1, double d2, double& f1,
                                         double& f2) {
   double u12 = u1 * u1, u22 = u2 * u2;
@@ -70,8 +71,8 @@ __device__ __forceinline__ void cgl_dnl(const CglPar& p, double u1, double u2, d
   double a21 = -4 * p.c5 * u2 * u12 * u1 - 3 * p.mu * u12 + (-4 * p.c5 * u22 * u2 - 2 * p.c3 * u2) * u1 - u22 * p.mu + p.nu;
   double a22 = -p.c5 * u12 * u12 + (-6 * p.c5 * u22 - p.c3) * u12 - 2 * p.mu * u1 * u2 - 5 * p.c5 * u22 * u22 -
                3 * p.c3 * u22 + p.r;
-  f1 = a11 * d1 + a12 * d2;
-  f2 = a21 * d1 + a22 * d2;
+  f1 = a11 * d1 + (TR ? a21 : a12) * d2;  // TR: J' (the Laplacian is symmetric, only this 2 x 2 block changes)
+  f2 = (TR ? a12 : a21) * d1 + a22 * d2;
 }
 // Dirichlet 5-point Laplacian (zero ghost cells; diagonal -2/h^2 everywhere, examples/cGL2d.jl:12-16)
 __device__ __forceinline__ double lap_dirichlet(const double* __restrict__ a, int i, int j, int nx, int ny, double cx,
@@ -83,7 +84,7 @@ __device__ __forceinline__ double lap_dirichlet(const double* __restrict__ a, in
   return s * (cx * (xm - 2.0 * c + xp) + cy * (ym - 2.0 * c + yp));
 }
 // Vector field / JVP at one grid point of one slice: base pointers to the slice's [u1;u2].
-template <int MODE>
+template <int MODE, bool TR = false>
 __device__ __forceinline__ void cgl_point(const CglPar& p, const double* __restrict__ u, const double* __restrict__ v,
                                           double s, int i, int j, int nx, int ny, double cx, double cy, double& o1,
                                           double& o2) {
@@ -94,7 +95,7 @@ __device__ __forceinline__ void cgl_point(const CglPar& p, const double* __restr
     o1 += lap_dirichlet(v, i, j, nx, ny, cx, cy, s);
     o2 += lap_dirichlet(v + n, i, j, nx, ny, cx, cy, s);
   } else {
-    cgl_dnl(p, u[g], u[g + n], s * v[g], s * v[g + n], o1, o2);
+    cgl_dnl<TR>(p, u[g], u[g + n], s * v[g], s * v[g + n], o1, o2);
     o1 += lap_dirichlet(v, i, j, nx, ny, cx, cy, s);
     o2 += lap_dirichlet(v + n, i, j, nx, ny, cx, cy, s);
   }
@@ -120,7 +121,8 @@ static __global__ void __launch_bounds__(256) k_cgl_apply(OpDesc op, const doubl
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
     int i = (int)(g % nx), j = (int)(g / nx);
     double o1, o2;
-    cgl_point<MODE>(p, op.u, in, s, i, j, nx, ny, op.cx, op.cy, o1, o2);
+    if (MODE == 0 && op.transpose) cgl_point<MODE, true>(p, op.u, in, s, i, j, nx, ny, op.cx, op.cy, o1, o2);
+    else cgl_point<MODE>(p, op.u, in, s, i, j, nx, ny, op.cx, op.cy, o1, o2);
     if (MODE == 0) {
       out[g] = op.a0 * s * in[g] + op.a1 * o1;
       out[g + n] = op.a0 * s * in[g + n] + op.a1 * o2;
@@ -266,6 +268,9 @@ static void fill_grid(bk_ctx* c, OpDesc& op) {
   op.bscale = 1.0;
   op.phi = c->phi;
   op.fcache = c->fcache;
+  op.cplx = c->cplx ? 1 : 0;
+  op.a0i = c->shift_imag;
+  op.transpose = c->transpose ? 1 : 0;
 }
 
 OpDesc bk_make_op(bk_ctx* c, double a0, double a1) {
@@ -284,6 +289,9 @@ OpDesc bk_make_residual_op(bk_ctx* c) {
   op.u = nullptr;
   op.a0 = 0;
   op.a1 = 1;
+  op.N = c->N0;  // F acts on the real state also in a BK_COMPLEX context
+  op.cplx = 0;
+  op.transpose = 0;
   return op;
 }
 
@@ -353,8 +361,35 @@ int bk_launch_residual(bk_ctx* c, const double* u, double* out) {
   return launch_kind<1>(c, op, u, nullptr, out);
 }
 
+// imaginary part of the shift on a split complex vector: out_re -= a0i s in_im, out_im += a0i s in_re
+static __global__ void __launch_bounds__(256) k_cshift(double* __restrict__ out, const double* __restrict__ in,
+                                                       const double* __restrict__ in_scale_ptr, double a0i, long long n0) {
+  const double s = (in_scale_ptr ? __ldg(in_scale_ptr) : 1.0) * a0i;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n0; g += (long long)gridDim.x * blockDim.x) {
+    const double xr = in[g], xi = in[g + n0];
+    out[g] -= s * xi;
+    out[g + n0] += s * xr;
+  }
+}
+
 int bk_launch_apply(bk_ctx* c, const OpDesc& op, const double* in, const double* sp, double* out) {
-  BK_TRY(launch_kind<0>(c, op, in, sp, out));
+  if (op.transpose) BK_CHECK(c, op.kind == BK_SH2D || op.kind == BK_SH3D || op.kind == BK_CGL2D, "J' is not available for this problem kind");
+  if (op.cplx) {
+    // ((a0 + i a0i) I + a1 J)(x + i y): the real operator on both halves, then the cross terms of the imaginary shift
+    OpDesc half = op;
+    half.cplx = 0;
+    half.N = op.N / 2;
+    half.bordered = 0;
+    BK_TRY(launch_kind<0>(c, half, in, sp, out));
+    BK_TRY(launch_kind<0>(c, half, in + half.N, sp, out + half.N));
+    if (op.a0i != 0.0) {
+      k_cshift<<<lin_grid(c, half.N), 256, 0, c->stream>>>(out, in, sp, op.a0i, half.N);
+      c->stats.kernel_launches++;
+      BK_CUDA(c, cudaGetLastError());
+    }
+  } else {
+    BK_TRY(launch_kind<0>(c, op, in, sp, out));
+  }
   if (op.bordered) {
     int g = lin_grid(c, op.N);
     if (g > c->gmax) g = c->gmax;
@@ -380,21 +415,35 @@ extern "C" int32_t bk_residual(bk_ctx* c, const double* u, double* out) {
   BK_ENTER(c);
   BkRange nvtx_range("bk_residual");
   double *du, *dout;
-  BK_TRY(bk_stage_in(c, u, c->N, 0, true, &du));
-  BK_TRY(bk_stage_in(c, out, c->N, 1, false, &dout));
+  BK_TRY(bk_stage_in(c, u, c->N0, 0, true, &du));
+  BK_TRY(bk_stage_in(c, out, c->N0, 1, false, &dout));
   BK_TRY(bk_launch_residual(c, du, dout));
-  return bk_stage_out(c, out, c->N, dout);
+  return bk_stage_out(c, out, c->N0, dout);
 }
 
 extern "C" int32_t bk_jac_set_state(bk_ctx* c, const double* u) {
   BK_ENTER(c);
   BK_CHECK(c, u != nullptr, "null state");
   cudaMemcpyKind kind = bk_is_device_ptr(u) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  BK_CUDA(c, cudaMemcpyAsync(c->u_state, u, 8 * (size_t)c->N, kind, c->stream));
-  if (kind == cudaMemcpyHostToDevice) c->stats.h2d_bytes += 8 * c->N;
+  BK_CUDA(c, cudaMemcpyAsync(c->u_state, u, 8 * (size_t)c->N0, kind, c->stream));
+  if (kind == cudaMemcpyHostToDevice) c->stats.h2d_bytes += 8 * c->N0;
   for (int i = 0; i < BK_MAX_PAR; ++i) c->jpar[i] = c->par[i];
   c->have_state = true;
   return bk_potrap_refresh_cache(c);
+}
+
+extern "C" int32_t bk_jac_set_shift_imag(bk_ctx* c, double a0_imag) {
+  BK_ENTER(c);
+  BK_CHECK(c, c->cplx || a0_imag == 0.0, "an imaginary shift needs a BK_COMPLEX context");
+  c->shift_imag = a0_imag;
+  return BK_OK;
+}
+
+extern "C" int32_t bk_jac_set_transpose(bk_ctx* c, int32_t on) {
+  BK_ENTER(c);
+  BK_CHECK(c, !on || c->kind == BK_SH2D || c->kind == BK_SH3D || c->kind == BK_CGL2D, "J' is not available for this problem kind");
+  c->transpose = on != 0;
+  return BK_OK;
 }
 
 extern "C" int32_t bk_jvp(bk_ctx* c, const double* v, double* out, double a0, double a1) {

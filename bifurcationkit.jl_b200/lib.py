@@ -13,16 +13,17 @@ CSRC = os.path.join(_HERE, "csrc")
 
 BK_OK, BK_NOT_CONVERGED = 0, 1
 BK_CHAN, BK_SH2D, BK_SH3D, BK_CGL2D, BK_POTRAP_CGL2D = 1, 2, 3, 4, 5
+BK_COMPLEX = 0x100  # OR-ed into the kind: complexified context, vectors [re; im]
 BK_PC_NONE, BK_PC_SH_DCT, BK_PC_CHAN_TRIDIAG, BK_PC_CGL_DST, BK_PC_POTRAP_CIRC = 0, 1, 2, 3, 4
 BK_SIDE_NONE, BK_SIDE_LEFT, BK_SIDE_RIGHT = 0, 1, 2
 BK_ORTH_CGS, BK_ORTH_CGS2 = 0, 1
 
 SYMBOLS = [
-    "bk_ctx_create", "bk_ctx_destroy", "bk_last_error", "bk_problem_size", "bk_set_params", "bk_get_stats",
+    "bk_ctx_create", "bk_ctx_destroy", "bk_last_error", "bk_problem_size", "bk_state_size", "bk_set_params", "bk_get_stats",
     "bk_set_timing", "bk_sync", "bk_stream",
     "bk_vec_alloc", "bk_vec_free", "bk_host_alloc", "bk_host_free", "bk_vec_upload", "bk_vec_download", "bk_vec_copy", "bk_vec_zero", "bk_vec_scale",
     "bk_vec_axpby", "bk_vec_dot", "bk_vec_norm2", "bk_vec_norminf", "bk_vec_diffdot",
-    "bk_residual", "bk_jac_set_state", "bk_jvp", "bk_precond_setup", "bk_precond_apply",
+    "bk_residual", "bk_jac_set_state", "bk_jvp", "bk_jac_set_shift_imag", "bk_jac_set_transpose", "bk_precond_setup", "bk_precond_apply",
     "bk_gmres", "bk_gmres2", "bk_bls_bordering", "bk_bls_matrixfree", "bk_bls_map",
     "bk_eigs_shift_invert", "bk_potrap_set_section", "bk_hessenberg_eig",
 ]
@@ -72,6 +73,7 @@ def load():
         "bk_ctx_create": [i32, i32, C.POINTER(i64), dp, i32, C.POINTER(C.c_void_p)],
         "bk_ctx_destroy": [C.c_void_p],
         "bk_problem_size": [C.c_void_p],
+        "bk_state_size": [C.c_void_p],
         "bk_set_params": [C.c_void_p, dp, i32],
         "bk_get_stats": [C.c_void_p, C.POINTER(Stats)],
         "bk_set_timing": [C.c_void_p, i32],
@@ -94,6 +96,8 @@ def load():
         "bk_residual": [C.c_void_p, vp, vp],
         "bk_jac_set_state": [C.c_void_p, vp],
         "bk_jvp": [C.c_void_p, vp, vp, dbl, dbl],
+        "bk_jac_set_shift_imag": [C.c_void_p, dbl],
+        "bk_jac_set_transpose": [C.c_void_p, i32],
         "bk_precond_setup": [C.c_void_p, i32, dbl, dbl],
         "bk_precond_apply": [C.c_void_p, vp, vp],
         "bk_gmres": [C.c_void_p, vp, vp, dbl, dbl, C.POINTER(GmresOpts), C.POINTER(i32), C.POINTER(i32), dp],
@@ -113,6 +117,7 @@ def load():
         f.argtypes = args
         f.restype = i32
     lib.bk_problem_size.restype = i64
+    lib.bk_state_size.restype = i64
     lib.bk_stream.restype = C.c_void_p
     lib.bk_last_error.argtypes = [C.c_void_p]
     lib.bk_last_error.restype = C.c_char_p

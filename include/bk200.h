@@ -38,7 +38,15 @@ enum {
   BK_SH2D = 2,   /* examples/SH2d-fronts.jl:13-34,124-127  params (l, nu)           dims (Nx,Ny)    */
   BK_SH3D = 3,   /* examples/SH3d.jl:16-53           params (l, nu)                  dims (Nx,Ny,Nz) */
   BK_CGL2D = 4,  /* examples/cGL2d.jl:6-22,262-318   params (r, mu, nu, c3, c5)      dims (Nx,Ny), N = 2 Nx Ny */
-  BK_POTRAP_CGL2D = 5 /* src/periodicorbit/PeriodicOrbitTrapeze.jl:209-330 over BK_CGL2D; dims (Nx,Ny,M), N = 2 Nx Ny M + 1 */
+  BK_POTRAP_CGL2D = 5, /* src/periodicorbit/PeriodicOrbitTrapeze.jl:209-330 over BK_CGL2D; dims (Nx,Ny,M), N = 2 Nx Ny M + 1 */
+  /* OR-ed into one of the kinds above (not BK_POTRAP_CGL2D): a COMPLEXIFIED context for the complex shifts of the Hopf
+   * minimally augmented system (src/codim2/MinAugHopf.jl:19-40, shift = Complex(0, -omega)) and complex eigenvector work.
+   * Unknowns are z = x + i y stored split, [x; y]: bk_problem_size = 2 N0, with N0 = bk_state_size the size of the real
+   * problem.  The operator of bk_jvp / bk_gmres / bk_gmres2 is ((a0 + i a0_imag) I + a1 J) z with the REAL Jacobian J (or its
+   * transpose) acting on both halves; a0_imag comes from bk_jac_set_shift_imag.  GMRES runs on the real-equivalent 2 N0 system
+   * (inner product Re<.,.>), the preconditioner is applied to both halves.  bk_residual / bk_jac_set_state still take real
+   * N0-vectors. */
+  BK_COMPLEX = 0x100
 };
 
 /* preconditioner kinds (the reference's Pl/Pr contract: src/Preconditioner.jl:11-37; the
@@ -89,6 +97,7 @@ int32_t bk_ctx_create(int32_t device, int32_t problem_kind, const int64_t dims[3
 int32_t bk_ctx_destroy(bk_ctx* ctx);
 const char* bk_last_error(bk_ctx* ctx);
 int64_t bk_problem_size(bk_ctx* ctx);                       /* N = number of unknowns of F */
+int64_t bk_state_size(bk_ctx* ctx);                         /* N0: length of u in bk_residual / bk_jac_set_state (= N unless BK_COMPLEX) */
 int32_t bk_set_params(bk_ctx* ctx, const double* params, int32_t n);
 int32_t bk_get_stats(bk_ctx* ctx, bk_stats* out);
 int32_t bk_set_timing(bk_ctx* ctx, int32_t on);              /* CUDA-event timing of the fused kernels and the preconditioner: 0 off, 1 every bk_gmres call, k > 1 every k-th call (the event records sit between PDL launches; sampling keeps the overhead small) */
@@ -117,6 +126,11 @@ int32_t bk_vec_diffdot(bk_ctx* ctx, const double* x, const double* x0, const dou
 int32_t bk_residual(bk_ctx* ctx, const double* u, double* out);        /* F(u; params)  (prob.VF.F, src/Problems.jl:133) */
 int32_t bk_jac_set_state(bk_ctx* ctx, const double* u);                /* J = jacobian(prob,u,params): copies u + current params (src/Problems.jl:98-101) */
 int32_t bk_jvp(bk_ctx* ctx, const double* v, double* out, double a0, double a1); /* out = a0 v + a1 J v (_axpy_op, src/LinearSolver.jl:46-62) */
+/* BK_COMPLEX contexts: imaginary part of the shift a0 of every later operator application (default 0) */
+int32_t bk_jac_set_shift_imag(bk_ctx* ctx, double a0_imag);
+/* apply J' instead of J from now on: apply_jacobian(prob, x, par, dx, true) / jacobian_adjoint (src/codim2/MinAugHopf.jl:79-81,
+ * 152-155).  SH2d / SH3d are self-adjoint (no-op), cGL2d transposes its 2 x 2 reaction block; BK_CHAN / BK_POTRAP_CGL2D: error */
+int32_t bk_jac_set_transpose(bk_ctx* ctx, int32_t on);
 
 /* ---- K6: preconditioner --------------------------------------------------------------------- */
 int32_t bk_precond_setup(bk_ctx* ctx, int32_t kind, double a0, double a1); /* SH_DCT: (L1 + a0 I)^-1; CGL_DST: (a0 I + a1 Lap)^-1 */

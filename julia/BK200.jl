@@ -32,11 +32,12 @@ end
 mutable struct Context
     handle::Ptr{Cvoid}
     N::Int
-    function Context(kind::Symbol, dims, lengths; krylov_m = 100, device = 0)
+    # complex = true: BK_COMPLEX context (include/bk200.h) -- vectors [re; im], complex shifts, for MinAugHopf.jl's solves
+    function Context(kind::Symbol, dims, lengths; krylov_m = 100, device = 0, complex = false)
         d = Int64[dims..., 1, 1][1:3]; L = Float64[lengths..., 1.0, 1.0][1:3]
         h = Ref{Ptr{Cvoid}}(C_NULL)
         st = ccall((:bk_ctx_create, lib), Int32, (Int32, Int32, Ptr{Int64}, Ptr{Float64}, Int32, Ptr{Ptr{Cvoid}}),
-                   device, KINDS[kind], d, L, krylov_m, h)
+                   device, KINDS[kind] | (complex ? 0x100 : 0), d, L, krylov_m, h)
         st < 0 && error("bk_ctx_create: " * unsafe_string(ccall((:bk_last_error, lib), Cstring, (Ptr{Cvoid},), h[])))
         c = new(h[], Int(ccall((:bk_problem_size, lib), Int64, (Ptr{Cvoid},), h[])))
         # bk_ctx_destroy frees every vector still alive (vec_live); the handle is nulled so that DeviceVec finalizers
@@ -156,6 +157,20 @@ function (l::GMRESB200)(J::Jac, rhs; a₀ = VI.Zero(), a₁ = VI.One(), kwargs..
                    c.handle, ptr(rhs), ptr(x), _num(a₀), _num(a₁), o, cv, it, rn))
     cv[] == 0 && @debug "bk_gmres iterated maxiter = $(it[]) times without achieving the desired tolerance."
     return x, cv[] != 0, Int(it[])
+end
+# complex right-hand side / shift on a BK_COMPLEX context: the `shift = Complex(0, -ω)` solves of src/codim2/MinAugHopf.jl:17.
+# J.ctx must have been created with complex = true; jacobian_adjoint maps to transpose!(ctx, true).
+transpose!(c::Context, on::Bool) = check(c, ccall((:bk_jac_set_transpose, lib), Int32, (Ptr{Cvoid}, Int32), c.handle, on ? 1 : 0))
+function (l::GMRESB200)(J::Jac, rhs::AbstractVector{<:Complex}; a₀ = VI.Zero(), a₁ = VI.One(), kwargs...)
+    c = J.ctx; s = ComplexF64(a₀ === VI.Zero() ? 0 : (a₀ === VI.One() ? 1 : a₀))
+    check(c, ccall((:bk_jac_set_shift_imag, lib), Int32, (Ptr{Cvoid}, Float64), c.handle, imag(s)))
+    x, cv, it = try
+        l(J, vcat(real(rhs), imag(rhs)); a₀ = real(s), a₁)
+    finally
+        ccall((:bk_jac_set_shift_imag, lib), Int32, (Ptr{Cvoid}, Float64), c.handle, 0.0)
+    end
+    n = length(rhs)
+    return complex.(x[1:n], x[n+1:2n]), cv, it
 end
 # two right-hand sides (src/LinearSolver.jl:15-19): one ABI crossing, (x1, x2, flag1 & flag2, (it1, it2))
 function (l::GMRESB200)(J::Jac, rhs1, rhs2; a₀ = VI.Zero(), a₁ = VI.One(), kwargs...)

@@ -483,3 +483,91 @@ def test_newton_fold_known_answers():
     sv = np.linalg.svd(Jc(s3.u, s3.p), compute_uv=False)
     assert sv[-1] < 1e-6 * sv[0] and np.linalg.norm(Fc(s3.u, s3.p)) < 1e-8
     assert p0 - 1e-9 <= s3.p < p0 + 0.02                          # the true fold lies at or just beyond the largest computed parameter
+
+
+# ------------------------------------------------------------------------------------------------ Hopf minimally augmented
+class DenseComplexProblem:
+    """cprob of codim2.HopfMinAug on dense matrices: J(x, p, transpose) -> callable on complex vectors"""
+
+    class Jc:
+        def __init__(self, M):
+            self.M = M
+
+        def __call__(self, z):
+            return self.M @ z
+
+    def __init__(self, Jfun):
+        self.Jfun = Jfun
+
+    def J(self, x, p, transpose=False):
+        M = np.asarray(self.Jfun(x, p), dtype=float)
+        return self.Jc(M.T.copy() if transpose else M)
+
+
+def _dense_cls(Jc, rhs, a0=0.0, a1=1.0):
+    n = Jc.M.shape[0]
+    return np.linalg.solve(a0 * np.eye(n) + a1 * Jc.M, rhs), True, 1
+
+
+def _dense_ls2(J, r1, r2):
+    return np.linalg.solve(J, r1), np.linalg.solve(J, r2), True, (1, 1)
+
+
+def test_hopf_border_known_answer_complex():
+    """The complex bordered system of the Hopf MA functional, test/linear_solvers/test_linear.jl:324-351:
+    J = [0 1 0; -1 0 0; 0 0 1], lambda = 1.01 x (its eigenvalue i), borders w (null vector of J' - conj(lambda)) and v:
+    the bordering elimination of codim2.HopfMinAug._border equals the explicit solve of [J - lambda I, w; v^H, 0] [x; s] = [0; 1]."""
+    bk = g.load_package()
+    J = np.array([[0.0, 1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    vals, vecs = np.linalg.eig(J)
+    k = int(np.argmin(abs(vals - 1j)))
+    lam, v = vals[k], vecs[:, k]
+    valt, vect = np.linalg.eig(J.T)
+    w = vect[:, int(np.argmin(abs(valt + 1j)))]
+    assert abs(np.linalg.det(J - lam * np.eye(3))) < 1e-12
+    lam = 1.01 * lam
+    J0 = np.block([[J - lam * np.eye(3), w[:, None]], [np.conj(v)[None, :], np.zeros((1, 1))]])
+    rhs = np.zeros(4, dtype=complex)
+    rhs[-1] = 1
+    explicit = np.linalg.solve(J0, rhs)
+    ma = bk.codim2.HopfMinAug(None, None, w, v, None, _dense_cls)
+    x, s = ma._border(DenseComplexProblem.Jc(J), -lam, w, v)
+    assert np.allclose(x, explicit[:-1], rtol=1e-10, atol=1e-12) and abs(s - explicit[-1]) < 1e-10 * abs(s)
+
+
+def test_newton_hopf_known_answers():
+    """newton_hopf (src/codim2/MinAugHopf.jl:19-188,258-283) on host arrays with dense solvers:
+    (i) Brusselator x' = a - (b+1) x + x^2 y, y' = b x - x^2 y: Hopf at b = 1 + a^2 with omega = a, equilibrium (a, b/a) moving
+    with the parameter (non-zero d_pF, sigma_x); (ii) cGL 2-D on 9 x 7 (examples/cGL2d.jl): trivial state, r = -lambda_1(Delta),
+    omega = nu, null vectors phi_11 x (1, -i)."""
+    bk = g.load_package()
+    P = bk.palc
+    opts = P.NewtonPar(tol=1e-9, max_iterations=15, linsolver=krylov.DefaultLS())
+    a = 1.3
+    F = lambda x, b: np.array([a - (b + 1) * x[0] + x[0] ** 2 * x[1], b * x[0] - x[0] ** 2 * x[1]])
+    J = lambda x, b: np.array([[-(b + 1) + 2 * x[0] * x[1], x[0] ** 2], [b - 2 * x[0] * x[1], -x[0] ** 2]])
+    bH = 1 + a * a
+    x0 = np.array([a, (bH + 0.2) / a]) + 0.01
+    vals, vecs = np.linalg.eig(J(x0, bH + 0.2))
+    k = int(np.argmax(vals.imag))
+    valt, vect = np.linalg.eig(J(x0, bH + 0.2).T)
+    kt = int(np.argmin(valt.imag))
+    sol = bk.codim2.newton_hopf(NumpyProblem(F, J, x0, bH + 0.2), DenseComplexProblem(J), x0, bH + 0.2, vals[k].imag,
+                                vecs[:, k], vect[:, kt], opts, _dense_ls2, _dense_cls)
+    assert sol.converged, sol.residuals
+    assert abs(sol.p - bH) < 1e-7 and abs(sol.omega - a) < 1e-7 and np.allclose(sol.u, [a, bH / a], atol=1e-7)
+    ev = np.linalg.eigvals(J(sol.u, sol.p))
+    assert np.max(abs(ev.real)) < 1e-6
+    # (ii)
+    gl = problems.GinzburgLandau2D(9, 7, 1.0, 0.8)
+    n = gl.N
+    Fg = lambda u, r: gl.F(u, r)
+    Jg = lambda u, r: np.column_stack([gl.dF(u, np.eye(n)[:, j], r) for j in range(n)])
+    rng = np.random.default_rng(3)
+    phi = gl.phi11()
+    zeta = np.concatenate([phi, -1j * phi]) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    u0 = 1e-3 * rng.standard_normal(n)
+    s2 = bk.codim2.newton_hopf(NumpyProblem(Fg, Jg, u0, gl.r_hopf() + 0.3), DenseComplexProblem(Jg), u0, gl.r_hopf() + 0.3, gl.nu + 0.2,
+                               zeta, zeta.copy(), opts, _dense_ls2, _dense_cls)
+    assert s2.converged, s2.residuals
+    assert abs(s2.p - gl.r_hopf()) < 1e-7 and abs(s2.omega - gl.nu) < 1e-7 and np.linalg.norm(s2.u) < 1e-8
