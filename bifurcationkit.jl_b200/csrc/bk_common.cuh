@@ -145,8 +145,7 @@ struct bk_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tpairs;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pc_pairs;  // one pair per preconditioner application (timing enabled)
   size_t pc_pairs_used = 0;
-  // cudaFuncAttributeMaxDynamicSharedMemorySize already granted per kernel ON THIS CONTEXT'S DEVICE (the attribute is per
-  // device: a process-wide cache would leave a second GPU's copy of the kernel at the 48 KB default)
+  // dynamic shared memory this context has already asked for, per kernel (first-level filter in front of bk_grant_smem)
   std::unordered_map<const void*, size_t> smem_attr;
   std::string err;
 };
@@ -213,13 +212,16 @@ int bk_launch_lincomb(bk_ctx* c, const double* basis, const double* scales, doub
                       const double* coef_dev);
 int bk_tmp(bk_ctx* c, int slot, double** out);  // lazily allocated ld-sized temporaries
 
-// grant `bytes` of dynamic shared memory to `kern` on the context's device (cached per context)
+// grant `bytes` of dynamic shared memory to `kern` on the context's device.  cudaFuncAttributeMaxDynamicSharedMemorySize is a
+// property of (device, kernel), shared by every context of the process: the grant only ever grows (bk_grant_smem keeps the
+// process-wide maximum under a mutex -- a context with a smaller Krylov dimension must not shrink what another one needs),
+// and the per-context map is just a lock-free first-level filter.
+void bk_grant_smem(int device, const void* kern, size_t bytes);
 template <typename K>
 static inline void bk_ensure_smem(bk_ctx* c, K kern, size_t bytes) {
   size_t& cur = c->smem_attr[(const void*)kern];
   if (bytes > cur) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    bk_grant_smem(c->device, (const void*)kern, bytes);
     cur = bytes;
   }
 }

@@ -3,6 +3,8 @@
 // device-resident state vector).
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include "bk_common.cuh"
 #include "bk_stencil.cuh"
@@ -14,6 +16,17 @@ int bk_fail(bk_ctx* c, int code, const char* what, const char* file, int line) {
     c->err = buf;
   }
   return code;
+}
+
+void bk_grant_smem(int device, const void* kern, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;  // (device, kernel) -> largest size set so far
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = granted[{device, kern}];
+  if (bytes <= cur) return;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cur = bytes;
 }
 
 bool bk_is_device_ptr(const void* p) {

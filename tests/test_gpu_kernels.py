@@ -279,3 +279,23 @@ def test_gmres_two_right_hand_sides(bk):
     assert oko and _rel(x1, o1) < 1e-7 and _rel(x2, o2) < 1e-7
     d1, d2, okd, itd = ls(ctx.jacobian(ctx.to_device(u)), ctx.to_device(r1), ctx.to_device(r2), a0=1.5, a1=-1.0)
     assert okd and np.array_equal(d1.numpy(), x1) and np.array_equal(d2.numpy(), x2)
+
+
+def test_two_contexts_with_different_krylov_dimensions_interleaved(bk):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (device, kernel), not to a context: a context with a small Krylov
+    dimension used between two solves of a large one must not shrink the large one's grant (found by the Hopf refinement, which
+    alternates between a real and a complexified context)."""
+    rng = np.random.default_rng(21)
+    dims = (64, 32)
+    sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
+    u = problems.sh2d_sol0(*dims, LX, LY)
+    rhs = rng.standard_normal(sh.N)
+    big = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=400, params=(-0.1, 1.3))
+    big.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    ls = bk.GMRESB200(reltol=1e-9, restart=400, maxiter=400, Pr=True)
+    x1, cv1, it1 = ls(big.jacobian(u), rhs)
+    small = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=10, params=(-0.1, 1.3))
+    small.precond_setup(bk.BK_PC_SH_DCT, 1.0)
+    bk.GMRESB200(reltol=1e-3, restart=10, maxiter=20, Pr=True)(small.jacobian(u), rhs)
+    x2, cv2, it2 = ls(big.jacobian(u), rhs)
+    assert cv1 and cv2 and it1 == it2 and np.array_equal(x1, x2)
