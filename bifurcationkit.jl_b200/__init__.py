@@ -10,7 +10,7 @@ from . import lib
 from .lib import (BK200Error, BK_CHAN, BK_SH2D, BK_SH3D, BK_CGL2D, BK_POTRAP_CGL2D, BK_COMPLEX, BK_PC_NONE, BK_PC_SH_DCT,
                   BK_PC_CHAN_TRIDIAG, BK_PC_CGL_DST, BK_PC_POTRAP_CIRC, build)
 from .core import (Context, DeviceVec, Jacobian, ComplexJacobian, GMRESB200, ComplexGMRESB200, BorderingBLSB200, MatrixFreeBLSB200, ShiftInvertB200,
-                   bls_map, make_opts, hessenberg_eig)
+                   bls_map, bls_map_block, make_opts, hessenberg_eig)
 from . import palc
 from . import segments
 from . import floquet

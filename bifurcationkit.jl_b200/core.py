@@ -320,6 +320,19 @@ class ComplexGMRESB200(GMRESB200):
         return cjoin(x), cv, it
 
 
+def _block_args(a, b, c, rhsb):
+    """tuples of border vectors -> pointer arrays; c -> m x m column-major (the Julia matrix layout); rhsb -> host doubles"""
+    a, b = (a,) if not isinstance(a, (tuple, list)) else tuple(a), (b,) if not isinstance(b, (tuple, list)) else tuple(b)
+    m = len(a)
+    assert m == len(b) and m in (1, 2), "block borders: one or two border vectors"
+    pa = (C.c_void_p * m)(*[_l.ptr(v) for v in a])
+    pb = (C.c_void_p * m)(*[_l.ptr(v) for v in b])
+    cm = np.asfortranarray(np.atleast_2d(np.asarray(c, dtype=np.float64)))
+    assert cm.shape == (m, m), "Linear bordered solver, wrong sizes!"
+    rb = None if rhsb is None else np.ascontiguousarray(np.atleast_1d(rhsb), dtype=np.float64)
+    return m, pa, pb, cm, rb, (a, b)  # the last entry keeps the vectors alive for the duration of the call
+
+
 class BorderingBLSB200:
     """src/LinearBorderSolver.jl:59-166."""
 
@@ -339,6 +352,22 @@ class BorderingBLSB200:
                                            _l.ptr(dX), C.byref(dl), C.byref(cv), it))
         return dX, dl.value, bool(cv.value), (it[0], it[1])
 
+    def solve_block(self, J, a, b, c, rhst, rhsb, shift=None):
+        """solve_bls_block(lbs::BorderingBLS, J, b, c, d, rhst, rhsb) (src/LinearBorderSolver.jl:173-206):
+        a / b tuples of one or two border vectors (columns / rows), c the m x m corner -> (u, p, converged, iters)"""
+        ctx = J.ctx
+        m, pa, pb, cm, rb, keep = _block_args(a, b, c, rhsb)
+        u = ctx._like(rhst)
+        sp = np.zeros(m)
+        o = self.solver.opts()
+        cv = C.c_int32()
+        it = (C.c_int32 * 3)()
+        dp = C.POINTER(C.c_double)
+        _chk(ctx, ctx.lib.bk_bls_block_bordering(ctx.handle, m, pa, pb, cm.ctypes.data_as(dp), _l.ptr(rhst), rb.ctypes.data_as(dp),
+                                                 0 if shift is None else 1, 0.0 if shift is None else shift, C.byref(o),
+                                                 _l.ptr(u), sp.ctypes.data_as(dp), C.byref(cv), it))
+        return u, sp, bool(cv.value), tuple(it[: m + 1])
+
 
 class MatrixFreeBLSB200:
     """src/LinearBorderSolver.jl:404-437 (rhs = vcat(R, n), one GMRES on the N+1 system)."""
@@ -355,6 +384,31 @@ class MatrixFreeBLSB200:
                                             0 if shift is None else 1, 0.0 if shift is None else shift, dotscale,
                                             C.byref(o), _l.ptr(dX), C.byref(dl), C.byref(cv), C.byref(it)))
         return dX, dl.value, bool(cv.value), it.value
+
+    def solve_block(self, J, a, b, c, rhst, rhsb, shift=None, dotscale=1.0):
+        """solve_bls_block(lbs::MatrixFreeBLS, J, a, b, c, rhst, rhsb; shift, dotp) (src/LinearBorderSolver.jl:440-450): one GMRES
+        on the (N + m) system through the tuple form of MatrixFreeBLSmap (:338-389)"""
+        ctx = J.ctx
+        m, pa, pb, cm, rb, keep = _block_args(a, b, c, rhsb)
+        u = ctx._like(rhst)
+        sp = np.zeros(m)
+        o = self.solver.opts()
+        cv, it = C.c_int32(), C.c_int32()
+        dp = C.POINTER(C.c_double)
+        _chk(ctx, ctx.lib.bk_bls_block_matrixfree(ctx.handle, m, pa, pb, cm.ctypes.data_as(dp), _l.ptr(rhst), rb.ctypes.data_as(dp),
+                                                  0 if shift is None else 1, 0.0 if shift is None else shift, dotscale, C.byref(o),
+                                                  _l.ptr(u), sp.ctypes.data_as(dp), C.byref(cv), C.byref(it)))
+        return u, sp, bool(cv.value), it.value
+
+
+def bls_map_block(J, a, b, c, x, shift=None, dotscale=1.0):
+    """MatrixFreeBLSmap(J, a::Tuple, b::Tuple, c::Matrix, shift, dot)(x) (src/LinearBorderSolver.jl:366-389), x of length N + m."""
+    ctx = J.ctx
+    m, pa, pb, cm, _, keep = _block_args(a, b, c, None)
+    out = ctx._like(x)
+    _chk(ctx, ctx.lib.bk_bls_block_map(ctx.handle, m, pa, pb, cm.ctypes.data_as(C.POINTER(C.c_double)), 0 if shift is None else 1,
+                                       0.0 if shift is None else shift, dotscale, _l.ptr(x), _l.ptr(out)))
+    return out
 
 
 def bls_map(J, a, b, c, x, shift=None, dotscale=1.0):

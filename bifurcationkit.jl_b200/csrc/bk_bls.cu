@@ -130,3 +130,145 @@ extern "C" int32_t bk_bls_matrixfree(bk_ctx* c, const double* dR, const double* 
   }
   return cv ? BK_OK : BK_NOT_CONVERGED;
 }
+
+// ------------------------------------------------------------------------------------------------ block / tuple borders
+// solve_bls_block (src/LinearBorderSolver.jl:168-206 BorderingBLS, :440-450 MatrixFreeBLS over the tuple form of
+// MatrixFreeBLSmap :338-389):   [ shift I + J   a_1 .. a_m ] [u]   [rhst]
+//                               [ dotp(b_i, .)      c      ] [p] = [rhsb]       m = 1 or 2 (the Hopf / codim-2 systems)
+// cmat is m x m, column-major (Julia layout).
+static int stage_borders(bk_ctx* c, int m, const double* const* a, const double* const* b, double* da[2], double* db[2]) {
+  static const int slot_a[2] = {6, 12}, slot_b[2] = {7, 13};
+  for (int i = 0; i < m; ++i) {
+    BK_TRY(bk_stage_in(c, a[i], c->N, slot_a[i], true, &da[i]));
+    BK_TRY(bk_stage_in(c, b[i], c->N, slot_b[i], true, &db[i]));
+  }
+  return BK_OK;
+}
+static void set_block_borders(OpDesc& op, int m, double* const da[2], double* const db[2], const double* cmat, int has_shift,
+                              double shift, double dotscale) {
+  op.bordered = m;
+  op.ba = da[0];
+  op.bb = db[0];
+  op.bc = cmat[0];
+  if (m == 2) {
+    op.ba2 = da[1];
+    op.bb2 = db[1];
+    op.bc10 = cmat[1];  // c[2,1]
+    op.bc01 = cmat[2];  // c[1,2]
+    op.bc11 = cmat[3];
+  }
+  op.bshift = has_shift ? shift : 0.0;
+  op.bscale = dotscale;
+}
+
+extern "C" int32_t bk_bls_block_map(bk_ctx* c, int32_t m, const double* const* a, const double* const* b, const double* cmat,
+                                    int32_t has_shift, double shift, double dotscale, const double* x, double* out) {
+  BK_ENTER(c);
+  BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
+  BK_CHECK(c, m == 1 || m == 2, "block borders: m must be 1 or 2");
+  BK_CHECK(c, a && b && cmat, "null border");
+  double *da[2], *db[2], *dx, *dout;
+  BK_TRY(stage_borders(c, m, a, b, da, db));
+  BK_TRY(bk_stage_in(c, x, c->N + m, 0, true, &dx));
+  BK_TRY(bk_stage_in(c, out, c->N + m, 1, false, &dout));
+  OpDesc op = bk_make_op(c, 0.0, 1.0);
+  set_block_borders(op, m, da, db, cmat, has_shift, shift, dotscale);
+  BK_TRY(bk_launch_apply(c, op, dx, nullptr, dout));
+  return bk_stage_out(c, out, c->N + m, dout);
+}
+
+extern "C" int32_t bk_bls_block_matrixfree(bk_ctx* c, int32_t m, const double* const* a, const double* const* b,
+                                           const double* cmat, const double* rhst, const double* rhsb, int32_t has_shift,
+                                           double shift, double dotscale, const bk_gmres_opts* opts, double* solu, double* solp,
+                                           int32_t* converged, int32_t* iters) {
+  BK_ENTER(c);
+  BkRange nvtx_range("bk_bls_block_matrixfree");
+  BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
+  BK_CHECK(c, opts != nullptr, "opts required");
+  BK_CHECK(c, m == 1 || m == 2, "block borders: m must be 1 or 2");
+  BK_CHECK(c, a && b && cmat && rhsb && solp, "null border");
+  const long long N = c->N;
+  double *da[2], *db[2], *d_R;
+  BK_TRY(stage_borders(c, m, a, b, da, db));
+  BK_TRY(bk_stage_in(c, rhst, N, 8, true, &d_R));
+  double *rhs, *sol;
+  BK_TRY(bk_tmp(c, 0, &rhs));
+  BK_TRY(bk_tmp(c, 1, &sol));
+  BK_TRY(bk_dev_copy(c, rhs, d_R, N));
+  BK_CUDA(c, cudaMemcpyAsync(rhs + N, rhsb, 8 * (size_t)m, cudaMemcpyHostToDevice, c->stream));  // rhs = vcat(rhst, rhsb)
+  OpDesc op = bk_make_op(c, 0.0, 1.0);
+  set_block_borders(op, m, da, db, cmat, has_shift, shift, dotscale);
+  int cv = 0, it = 0;
+  int st = bk_gmres_dev(c, op, rhs, sol, opts, &cv, &it, nullptr);
+  if (st < 0) return st;
+  BK_CUDA(c, cudaMemcpyAsync(c->red_pinned + 1, sol + N, 8 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < m; ++i) solp[i] = c->red_pinned[1 + i];
+  if (converged) *converged = cv;
+  if (iters) *iters = it;
+  if (bk_is_device_ptr(solu)) {
+    BK_TRY(bk_dev_copy(c, solu, sol, N));
+    BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  } else {
+    BK_TRY(bk_stage_out(c, solu, N, sol));
+  }
+  return cv ? BK_OK : BK_NOT_CONVERGED;
+}
+
+extern "C" int32_t bk_bls_block_bordering(bk_ctx* c, int32_t m, const double* const* a, const double* const* b,
+                                          const double* cmat, const double* rhst, const double* rhsb, int32_t has_shift,
+                                          double shift, const bk_gmres_opts* opts, double* solu, double* solp,
+                                          int32_t* converged, int32_t iters[3]) {
+  BK_ENTER(c);
+  BkRange nvtx_range("bk_bls_block_bordering");
+  BK_CHECK(c, c->have_state, "bk_jac_set_state must be called first");
+  BK_CHECK(c, opts != nullptr, "opts required");
+  BK_CHECK(c, m == 1 || m == 2, "block borders: m must be 1 or 2");
+  BK_CHECK(c, a && b && cmat && rhsb && solp, "null border");
+  const long long N = c->N;
+  double *da[2], *db[2], *d_R, *d_u;
+  BK_TRY(stage_borders(c, m, a, b, da, db));
+  BK_TRY(bk_stage_in(c, rhst, N, 8, true, &d_R));
+  BK_TRY(bk_stage_in(c, solu, N, 9, false, &d_u));
+  // x1 = A^-1 rhst, x2_j = A^-1 a_j;  S = c - [<b_i, x2_j>],  h = rhsb - [<b_i, x1>],  p = S \ h,  u = x1 - sum p_j x2_j
+  OpDesc op = bk_make_op(c, has_shift ? shift : 0.0, 1.0);
+  int cv = 1, ci = 0, it = 0;
+  int st = bk_gmres_dev(c, op, d_R, d_u, opts, &ci, &it, nullptr);
+  if (st < 0) return st;
+  cv &= ci;
+  if (iters) iters[0] = it;
+  double* x2[2] = {nullptr, nullptr};
+  for (int j = 0; j < m; ++j) {
+    BK_TRY(bk_tmp(c, j, &x2[j]));
+    st = bk_gmres_dev(c, op, da[j], x2[j], opts, &ci, &it, nullptr);
+    if (st < 0) return st;
+    cv &= ci;
+    if (iters) iters[1 + j] = it;
+  }
+  double S[4] = {0, 0, 0, 0}, h[2] = {0, 0};
+  for (int i = 0; i < m; ++i) {
+    double d = 0;
+    BK_TRY(bk_dev_dot(c, db[i], d_u, N, &d));
+    h[i] = rhsb[i] - d;
+    for (int j = 0; j < m; ++j) {
+      BK_TRY(bk_dev_dot(c, db[i], x2[j], N, &d));
+      S[i + 2 * j] = cmat[i + m * j] - d;
+    }
+  }
+  double p[2] = {0, 0};
+  if (m == 1) {
+    p[0] = h[0] / S[0];
+  } else {
+    const double det = S[0] * S[3] - S[2] * S[1];
+    p[0] = (h[0] * S[3] - S[2] * h[1]) / det;
+    p[1] = (S[0] * h[1] - S[1] * h[0]) / det;
+  }
+  for (int j = 0; j < m; ++j) {
+    BK_TRY(bk_dev_axpby(c, d_u, -p[j], x2[j], 1.0, N));
+    solp[j] = p[j];
+  }
+  if (converged) *converged = cv;
+  BK_TRY(bk_stage_out(c, solu, N, d_u));
+  BK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return cv ? BK_OK : BK_NOT_CONVERGED;
+}

@@ -29,10 +29,15 @@ struct OpDesc {
   double a0, a1;         // a0 I + a1 J
   long long N;           // unknowns of the un-bordered problem
   // bordered map:  out.u = Op(x.u) + x.p * ba (+ bshift * x.u);  out.p = bscale*<bb, x.u> + bc * x.p
-  int bordered;
+  int bordered;          // number of borders: 0, 1 or 2
   const double* ba;
   const double* bb;
   double bc, bshift, bscale;
+  // second border of the block / tuple form (src/LinearBorderSolver.jl:338-389): x.p and out.p have two entries,
+  //   out.u += x.p[1] ba2;   out.p = bscale [<bb, x.u>; <bb2, x.u>] + [bc bc01; bc10 bc11] x.p
+  const double* ba2;
+  const double* bb2;
+  double bc01, bc10, bc11;
   // potrap extras
   const double* phi;     // section (length N-1)
   const double* fcache;  // F(x_i) cache, M slices (device)

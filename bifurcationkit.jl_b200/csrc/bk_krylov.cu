@@ -328,6 +328,7 @@ static inline int chunk_grid(long long n) { return (int)((n + BK_TILE - 1) / BK_
 // iteration than stand-alone JVP + TMA-ring dots, so "automatic" keeps it off until a TMA-ring 3-D kernel exists.
 static bool fused_available(const OpDesc& op, int fused_mode = 2) {
   if (op.cplx) return false;  // the fused kernels tile one real grid; a split complex vector takes the two-launch path
+  if (op.bordered > 1) return false;  // block borders: stencil + k_tail2
   if (op.kind == BK_SH2D) return !op.bordered || (op.nx % 2 == 0);
   if (op.kind == BK_SH3D) return !op.bordered && fused_mode >= 2;
   return false;
@@ -502,8 +503,10 @@ static int init_residual(bk_ctx* c, const OpDesc& op, const bk_gmres_opts* o, lo
 
 int bk_gmres_dev(bk_ctx* c, const OpDesc& op, const double* rhs, double* x, const bk_gmres_opts* o, int* converged,
                  int* iters, double* resnorm) {
-  const long long n = op.N + (op.bordered ? 1 : 0);
-  BK_CHECK(c, n + 1 <= c->ld + 1, "system larger than the context");
+  const long long n = op.N + op.bordered;
+  BK_CHECK(c, n <= c->ld, "system larger than the context");
+  // the TMA rows of k2_dots / k2_update are read in pairs: an odd length needs one zero pad element behind it
+  BK_CHECK(c, (n % 2 == 0) || n + 1 <= c->ld, "no pad element left for an odd-sized bordered system");
   int restart = o->restart;
   if (restart > c->m) restart = c->m;
   if ((long long)restart > n) restart = (int)n;

@@ -251,6 +251,59 @@ static __global__ void __launch_bounds__(256) k_tail(OpDesc op, const double* __
   }
 }
 
+// two borders (block / tuple MatrixFreeBLSmap, src/LinearBorderSolver.jl:338-389): the same pass with two dot products
+static __global__ void __launch_bounds__(256) k_tail2(OpDesc op, const double* __restrict__ in,
+                                                      const double* __restrict__ in_scale_ptr, double* __restrict__ out,
+                                                      long long n, double* __restrict__ partials, unsigned int* counter) {
+  __shared__ double s_w[16];
+  __shared__ int s_flag;
+  const double s = in_scale_ptr ? __ldg(in_scale_ptr) : 1.0;
+  const double xp0 = s * in[n], xp1 = s * in[n + 1];
+  double acc0 = 0.0, acc1 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = in[i];
+    acc0 = fma(v, op.bb[i], acc0);
+    acc1 = fma(v, op.bb2[i], acc1);
+    out[i] += xp0 * op.ba[i] + xp1 * op.ba2[i] + op.bshift * s * v;
+  }
+  acc0 = bk_warp_sum(acc0);
+  acc1 = bk_warp_sum(acc1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_w[wid] = acc0;
+    s_w[8 + wid] = acc1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0;
+    for (int k = 0; k < 8; ++k) t += s_w[8 * threadIdx.x + k];
+    partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+  }
+  if (bk_last_block(counter, &s_flag)) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+      t0 += __ldcg(partials + k);
+      t1 += __ldcg(partials + gridDim.x + k);
+    }
+    t0 = bk_warp_sum(t0);
+    t1 = bk_warp_sum(t1);
+    if (lane == 0) {
+      s_w[wid] = t0;
+      s_w[8 + wid] = t1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r0 = 0, r1 = 0;
+      for (int k = 0; k < 8; ++k) {
+        r0 += s_w[k];
+        r1 += s_w[8 + k];
+      }
+      out[n] = s * op.bscale * r0 + op.bc * xp0 + op.bc01 * xp1;
+      out[n + 1] = s * op.bscale * r1 + op.bc10 * xp0 + op.bc11 * xp1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static void fill_grid(bk_ctx* c, OpDesc& op) {
   op.kind = c->kind;
@@ -266,6 +319,8 @@ static void fill_grid(bk_ctx* c, OpDesc& op) {
   op.ba = op.bb = nullptr;
   op.bc = op.bshift = 0.0;
   op.bscale = 1.0;
+  op.ba2 = op.bb2 = nullptr;
+  op.bc01 = op.bc10 = op.bc11 = 0.0;
   op.phi = c->phi;
   op.fcache = c->fcache;
   op.cplx = c->cplx ? 1 : 0;
@@ -393,7 +448,8 @@ int bk_launch_apply(bk_ctx* c, const OpDesc& op, const double* in, const double*
   if (op.bordered) {
     int g = lin_grid(c, op.N);
     if (g > c->gmax) g = c->gmax;
-    k_tail<1><<<g, 256, 0, c->stream>>>(op, in, sp, out, op.N, 0.0, 0, c->partials, c->counters + 9);
+    if (op.bordered == 2) k_tail2<<<g, 256, 0, c->stream>>>(op, in, sp, out, op.N, c->partials, c->counters + 9);
+    else k_tail<1><<<g, 256, 0, c->stream>>>(op, in, sp, out, op.N, 0.0, 0, c->partials, c->counters + 9);
     c->stats.kernel_launches++;
     BK_CUDA(c, cudaGetLastError());
   }

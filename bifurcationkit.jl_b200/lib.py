@@ -25,6 +25,7 @@ SYMBOLS = [
     "bk_vec_axpby", "bk_vec_dot", "bk_vec_norm2", "bk_vec_norminf", "bk_vec_diffdot",
     "bk_residual", "bk_jac_set_state", "bk_jvp", "bk_jac_set_shift_imag", "bk_jac_set_transpose", "bk_precond_setup", "bk_precond_apply",
     "bk_gmres", "bk_gmres2", "bk_bls_bordering", "bk_bls_matrixfree", "bk_bls_map",
+    "bk_bls_block_bordering", "bk_bls_block_matrixfree", "bk_bls_block_map",
     "bk_eigs_shift_invert", "bk_potrap_set_section", "bk_hessenberg_eig",
 ]
 
@@ -107,6 +108,11 @@ def load():
         "bk_bls_matrixfree": [C.c_void_p, vp, vp, dbl, vp, dbl, dbl, dbl, i32, dbl, dbl, C.POINTER(GmresOpts),
                               vp, dp, C.POINTER(i32), C.POINTER(i32)],
         "bk_bls_map": [C.c_void_p, vp, vp, dbl, i32, dbl, dbl, vp, vp],
+        "bk_bls_block_bordering": [C.c_void_p, i32, C.POINTER(vp), C.POINTER(vp), dp, vp, dp, i32, dbl, C.POINTER(GmresOpts),
+                                   vp, dp, C.POINTER(i32), C.POINTER(i32)],
+        "bk_bls_block_matrixfree": [C.c_void_p, i32, C.POINTER(vp), C.POINTER(vp), dp, vp, dp, i32, dbl, dbl, C.POINTER(GmresOpts),
+                                    vp, dp, C.POINTER(i32), C.POINTER(i32)],
+        "bk_bls_block_map": [C.c_void_p, i32, C.POINTER(vp), C.POINTER(vp), dp, i32, dbl, dbl, vp, vp],
         "bk_eigs_shift_invert": [C.c_void_p, dbl, i32, i32, dbl, i32, C.POINTER(GmresOpts), vp, dp, dp, vp,
                                  C.POINTER(i32), C.POINTER(i32)],
         "bk_potrap_set_section": [C.c_void_p, vp, vp],

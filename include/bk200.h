@@ -156,6 +156,21 @@ int32_t bk_bls_matrixfree(bk_ctx* ctx, const double* dR, const double* dzu, doub
 int32_t bk_bls_map(bk_ctx* ctx, const double* a, const double* b, double c, int32_t has_shift, double shift, double dotscale,
                    const double* x, double* out);
 
+/* block / tuple borders, m = 1 or 2 (solve_bls_block, src/LinearBorderSolver.jl:168-206 and :440-450 over the tuple form of
+ * MatrixFreeBLSmap :338-389 -- the bordered systems of the Hopf / codim-2 formulations):
+ *   [ shift I + J   a[0] .. a[m-1] ] [solu]   [rhst]
+ *   [ dotp(b[i], .)       c        ] [solp] = [rhsb],   c is m x m column-major, rhsb / solp are HOST arrays of m doubles,
+ * a[i] / b[i] / rhst / solu are host or device vectors of length N.  bordering: m + 1 solves with J and the Schur complement
+ * (plain <.,.>, as the reference's VI.inner); matrixfree: one GMRES on the (N + m) system, dotp = dotscale <.,.>. */
+int32_t bk_bls_block_bordering(bk_ctx* ctx, int32_t m, const double* const* a, const double* const* b, const double* c,
+                               const double* rhst, const double* rhsb, int32_t has_shift, double shift,
+                               const bk_gmres_opts* opts, double* solu, double* solp, int32_t* converged, int32_t iters[3]);
+int32_t bk_bls_block_matrixfree(bk_ctx* ctx, int32_t m, const double* const* a, const double* const* b, const double* c,
+                                const double* rhst, const double* rhsb, int32_t has_shift, double shift, double dotscale,
+                                const bk_gmres_opts* opts, double* solu, double* solp, int32_t* converged, int32_t* iters);
+int32_t bk_bls_block_map(bk_ctx* ctx, int32_t m, const double* const* a, const double* const* b, const double* c,
+                         int32_t has_shift, double shift, double dotscale, const double* x, double* out); /* x, out: N + m */
+
 /* ---- S10: shift-invert Arnoldi (src/EigSolver.jl:246-266; inner solver = bk_gmres with a0=-sigma)
  *   vals sorted by decreasing real part; vecs (N x nev, column-major, real Schur/Ritz vectors; complex pairs
  *   as (re, im) consecutive columns) may be NULL. */

@@ -105,3 +105,56 @@ class MatrixBLS:
             A[N, N] = xip * dzp
             sol = np.linalg.solve(A, np.concatenate([R, [n]]))
         return sol[:-1], sol[-1], True, 1
+
+
+class MatrixFreeBLSmapBlock:
+    """Tuple / block form, src/LinearBorderSolver.jl:366-389: x = [xu; xp], m = len(a) entries in xp;
+    out.u = J xu + sum_i xp[i] a[i] (+ shift xu);  out.p = c xp + [dot(b[i], xu)]."""
+
+    def __init__(self, J, a, b, c, shift, dot):
+        self.J, self.a, self.b, self.c, self.shift, self.dot = J, tuple(a), tuple(b), np.atleast_2d(np.asarray(c, float)), shift, dot
+
+    def __call__(self, x):
+        m = len(self.a)
+        xu, xp = x[:-m], x[-m:]
+        out = np.empty_like(x)
+        out[:-m] = _apply(self.J, xu)
+        for i in range(m):
+            out[:-m] += self.a[i] * xp[i]
+        if self.shift is not None:
+            out[:-m] += self.shift * xu
+        out[-m:] = self.c @ xp
+        for i in range(m):
+            out[len(xu) + i] += self.dot(self.b[i], xu)
+        return out
+
+
+def solve_bls_block_bordering(solver, J, b, c, d, rhst, rhsb, shift=None):
+    """solve_bls_block(lbs::BorderingBLS, J, b, c, d, rhst, rhsb), src/LinearBorderSolver.jl:173-206: b columns, c rows, d corner."""
+    m = np.atleast_2d(d).shape[0]
+    if not (len(b) == len(c) == m):
+        raise ValueError("Linear bordered solver, wrong sizes!")
+    kw = {} if shift is None else {"a0": shift}
+    x1, cv, it = solver(J, rhst, **kw)
+    x2s, its = [], []
+    for bi in b:
+        x2, flag, i2 = solver(J, bi, **kw)
+        x2s.append(x2)
+        its.append(i2)
+        cv = cv and flag
+    d = np.atleast_2d(np.asarray(d, float))
+    S = np.array([[d[i, j] - np.dot(c[i], x2s[j]) for j in range(m)] for i in range(m)])
+    h = np.array([rhsb[i] - np.dot(c[i], x1) for i in range(m)])
+    u2 = np.linalg.solve(S, h)
+    u1 = x1.copy()
+    for i in range(m):
+        u1 -= u2[i] * x2s[i]
+    return u1, u2, cv, (it, *its)
+
+
+def solve_bls_block_matrixfree(solver, J, a, b, c, rhst, rhsb, shift=None, dotp=np.dot):
+    """solve_bls_block(lbs::MatrixFreeBLS, J, a, b, c, rhst, rhsb; shift, dotp), src/LinearBorderSolver.jl:440-450."""
+    lmap = MatrixFreeBLSmapBlock(J, a, b, c, shift, dotp)
+    m = len(a)
+    sol, cv, it = solver(lmap, np.concatenate([rhst, np.atleast_1d(rhsb)]))
+    return sol[:-m], sol[-m:], cv, it

@@ -159,3 +159,28 @@ def test_dst_helmholtz_precond_inverts_shifted_dirichlet_laplacian():
         ref = spl.spsolve((a0 * sp.identity(nx * ny) + a1 * lap).tocsc(), v)
         got = precond.dst_helmholtz_precond(nx, ny, np.pi, np.pi / 2, a0, a1)(v)
         assert np.linalg.norm(got - ref) < 1e-13 * np.linalg.norm(ref)
+
+
+def test_block_bordered_solvers_oracle_vs_dense():
+    """solve_bls_block, both forms (src/LinearBorderSolver.jl:173-206, 440-450), as exercised by test/linear_solvers/test_linear.jl:300-320
+    (random J, a, b, c): against the explicit (N + 2) x (N + 2) matrix; the tuple map (:366-389) against the same matrix."""
+    obls = bls
+    rng = np.random.default_rng(5)
+    N = 40
+    J = rng.standard_normal((N, N)) + 6 * np.eye(N)
+    a = (rng.standard_normal(N), rng.standard_normal(N))
+    b = (rng.standard_normal(N), rng.standard_normal(N))
+    c = rng.standard_normal((2, 2))
+    rhst, rhsb = rng.standard_normal(N), rng.standard_normal(2)
+    for shift in (None, 0.4):
+        A = np.block([[J + (0 if shift is None else shift) * np.eye(N), np.column_stack(a)], [np.vstack(b), c]])
+        ex = np.linalg.solve(A, np.concatenate([rhst, rhsb]))
+        u, p, cv, it = obls.solve_bls_block_bordering(krylov.DefaultLS(), J, a, b, c, rhst, rhsb, shift=shift)
+        assert cv and np.allclose(u, ex[:N], atol=1e-10) and np.allclose(p, ex[N:], atol=1e-10)
+        gm = krylov.GMRESIterativeSolvers(reltol=1e-12, restart=N + 2, maxiter=200)
+        u, p, cv, it = obls.solve_bls_block_matrixfree(gm, J, a, b, c, rhst, rhsb, shift=shift)
+        assert cv and np.allclose(u, ex[:N], atol=1e-8) and np.allclose(p, ex[N:], atol=1e-8)
+        x = rng.standard_normal(N + 2)
+        assert np.allclose(obls.MatrixFreeBLSmapBlock(J, a, b, c, shift, np.dot)(x), A @ x, atol=1e-12)
+    with pytest.raises(ValueError):
+        obls.solve_bls_block_bordering(krylov.DefaultLS(), J, a, b[:1], c, rhst, rhsb)
