@@ -223,6 +223,28 @@ function (b::MatrixFreeBLSB200)(J::Jac, dR, dzu, dzp::T, R, n::T, ξu = 1, ξp =
     return dX, dl[], cv[] != 0, Int(it[])
 end
 
+# solve_bls_block with one or two borders (src/LinearBorderSolver.jl:173-206 and :440-450): a, b tuples of vectors, c the m x m corner
+function BK.solve_bls_block(lbs::BorderingBLSB200, J::Jac, a::NTuple{M}, b::NTuple{M}, c::AbstractMatrix, rhst, rhsb; shift = nothing) where {M}
+    (1 <= M <= 2 && size(c) == (M, M)) || error("Linear bordered solver, wrong sizes!")
+    ctx = J.ctx; u = like(ctx, rhst); o = Ref(opts(lbs.solver))
+    pa = Ptr{Float64}[ptr(v) for v in a]; pb = Ptr{Float64}[ptr(v) for v in b]
+    cm = Matrix{Float64}(c); rb = collect(Float64, rhsb); sp = zeros(M); cv = Ref{Int32}(0); it = zeros(Int32, 3)
+    GC.@preserve a b check(ctx, ccall((:bk_bls_block_bordering, lib), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{GmresOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        ctx.handle, M, pa, pb, cm, ptr(rhst), rb, isnothing(shift) ? 0 : 1, isnothing(shift) ? 0.0 : shift, o, ptr(u), sp, cv, it))
+    return u, sp, cv[] != 0, Tuple(Int.(it[1:M+1]))
+end
+function BK.solve_bls_block(lbs::MatrixFreeBLSB200, J::Jac, a::NTuple{M}, b::NTuple{M}, c::AbstractMatrix, rhst, rhsb; shift = nothing, dotp = dot) where {M}
+    (1 <= M <= 2 && size(c) == (M, M)) || error("Linear bordered solver, wrong sizes!")
+    ctx = J.ctx; u = like(ctx, rhst); o = Ref(opts(lbs.solver))
+    pa = Ptr{Float64}[ptr(v) for v in a]; pb = Ptr{Float64}[ptr(v) for v in b]
+    cm = Matrix{Float64}(c); rb = collect(Float64, rhsb); sp = zeros(M); cv = Ref{Int32}(0); it = Ref{Int32}(0)
+    GC.@preserve a b check(ctx, ccall((:bk_bls_block_matrixfree, lib), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64, Ptr{GmresOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        ctx.handle, M, pa, pb, cm, ptr(rhst), rb, isnothing(shift) ? 0 : 1, isnothing(shift) ? 0.0 : shift, _dotscale(dotp, ctx.N), o, ptr(u), sp, cv, it))
+    return u, sp, cv[] != 0, Int(it[])
+end
+
 # ---- AbstractEigenSolver (src/EigSolver.jl:4-8,246-266) ----------------------------------------------------------------
 struct ShiftInvertB200 <: BK.AbstractEigenSolver
     ctx::Context
