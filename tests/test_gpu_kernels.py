@@ -320,9 +320,11 @@ def test_block_bordered_solvers(bk, kind):
         dims = (32, 16) if kind == "sh2d" else (15, 9)          # odd N: the (N + 2)-vectors use the pad element behind them
         sh = problems.SwiftHohenberg(dims, (LX, LY), l=-0.1, nu=1.3)
         N, u, dF = sh.N, problems.sh2d_sol0(*dims, LX, LY) + 0.1 * rng.standard_normal(sh.N), sh.dF
-        ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=200, params=(-0.1, 1.3))
+        # Krylov dimension >= N + 2: no restarts.  J + 0.3 I is indefinite here and GMRES(200) stagnates on it (measured: full GMRES
+        # needs 211-222 iterations for 1e-8..1e-12, GMRES(200) 500+ and GMRES(100) does not get below 1e-7 in 600)
+        ctx = bk.Context(bk.BK_SH2D, dims, (LX, LY), krylov_m=560, params=(-0.1, 1.3))
         ctx.precond_setup(bk.BK_PC_SH_DCT, 1.0)
-        ls = bk.GMRESB200(reltol=1e-12, restart=200, maxiter=600, Pr=True, orth="cgs2")
+        ls = bk.GMRESB200(reltol=1e-12, restart=560, maxiter=1120, Pr=True, orth="cgs2")
     lm = bk.GMRESB200(reltol=1e-10, restart=ls.restart, maxiter=ls.maxiter, Pr=ls.Pr, orth="cgs2")
     Jd = np.column_stack([dF(u, np.eye(N)[:, j]) for j in range(N)])
     a = (rng.standard_normal(N), rng.standard_normal(N))
