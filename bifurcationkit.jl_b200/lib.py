@@ -26,7 +26,7 @@ SYMBOLS = [
     "bk_residual", "bk_jac_set_state", "bk_jvp", "bk_jac_set_shift_imag", "bk_jac_set_transpose", "bk_precond_setup", "bk_precond_apply",
     "bk_gmres", "bk_gmres2", "bk_bls_bordering", "bk_bls_matrixfree", "bk_bls_map",
     "bk_bls_block_bordering", "bk_bls_block_matrixfree", "bk_bls_block_map",
-    "bk_eigs_shift_invert", "bk_potrap_set_section", "bk_hessenberg_eig",
+    "bk_eigs_shift_invert", "bk_potrap_set_section", "bk_hessenberg_eig", "bk_palc_run",
 ]
 
 
@@ -40,6 +40,23 @@ class Stats(C.Structure):
                 ("last_fused_ms", C.c_double), ("last_fused_bytes", C.c_int64), ("last_fused_launches", C.c_int64),
                 ("total_fused_ms", C.c_double), ("total_fused_bytes", C.c_int64), ("total_fused_launches", C.c_int64),
                 ("cgs_fallbacks", C.c_int64), ("total_precond_ms", C.c_double), ("total_precond_applies", C.c_int64)]
+
+
+class PalcOpts(C.Structure):
+    """bk_palc_opts (include/bk200.h)"""
+    _fields_ = [(k, C.c_double) for k in ("ds", "dsmin", "dsmax", "a", "p_min", "p_max", "theta", "eta", "newton_tol", "fd_eps", "bls_tol")] + \
+               [(k, C.c_int32) for k in ("max_steps", "newton_maxit", "lens", "tangent", "bls", "bls_check_precision", "bls_k", "normc")]
+
+
+class PalcResult(C.Structure):
+    """bk_palc_result"""
+    _fields_ = [("nrows", C.c_int32), ("steps", C.c_int32), ("nfail", C.c_int32), ("stopped", C.c_int32),
+                ("work_newton", C.c_int64), ("work_linear", C.c_int64), ("p_final", C.c_double), ("ds_final", C.c_double)]
+
+
+BK_PALC_ROW = 6
+# int32_t (*bk_palc_callback)(void* user, int32_t step, const double* row, const double* z_u /* device */, double z_p)
+PalcCallback = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_void_p, C.c_double)
 
 
 class BK200Error(RuntimeError):
@@ -117,6 +134,8 @@ def load():
                                  C.POINTER(i32), C.POINTER(i32)],
         "bk_potrap_set_section": [C.c_void_p, vp, vp],
         "bk_hessenberg_eig": [dp, i32, i32, dp, dp, dp, dp],
+        "bk_palc_run": [C.c_void_p, C.POINTER(PalcOpts), C.POINTER(GmresOpts), vp, dbl, vp, dbl, dp, i32, PalcCallback, C.c_void_p,
+                        vp, C.POINTER(PalcResult)],
     }
     for name, args in sig.items():
         f = getattr(lib, name)

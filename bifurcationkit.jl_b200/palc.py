@@ -248,7 +248,7 @@ def step_size_control(ds, converged, itnewton, contpar):
     else:
         Nmax = contpar.newton_options.max_iterations
         factor = (Nmax - itnewton) / Nmax
-        dsnew = ds * (1 + contpar.a * factor**2)
+        dsnew = ds * (1 + contpar.a * (factor * factor))  # factor^2 is a literal power in Julia: x * x
     dsnew = math.copysign(min(max(abs(dsnew), contpar.dsmin), contpar.dsmax), dsnew)
     return dsnew, False
 
@@ -400,3 +400,52 @@ def continuation(prob, alg, contpar, normC=V.norm2, u1=None, p1=None, verbose=Fa
                 _bordered_tangent(prob, st, theta, bls)
         _predict(st)
     return rows, st
+
+
+def continuation_native(prob, alg, contpar, normC=V.norm2, u1=None, p1=None, callback=None, max_rows=None):
+    """The same branch through ONE C-ABI call: bk_palc_run (include/bk200.h; the loop above restated as host C++ inside
+    libbk200.so, csrc/bk_palc_loop.hpp) -- same kernels in the same order, so the rows are bit-identical to `continuation`
+    with a device-resident state; what disappears is the host-language dispatch between the kernels (a dozen ABI crossings and
+    a few allocations per Newton iteration).  `prob.u0` / `u1` may be NumPy arrays (uploaded once) or DeviceVecs.
+    detect_bifurcation = 0 only.  `callback(step, row_dict, z_u_device_pointer, z_p)` -> False stops the run.
+    Returns (rows, info): rows as `continuation`, info = dict(steps, nfail, stopped, work_newton, work_linear, p, ds, u)."""
+    import ctypes as C
+    from . import lib as _l
+    from .core import _chk, BorderingBLSB200, MatrixFreeBLSB200
+    ctx = prob.ctx
+    assert contpar.detect_bifurcation == 0 or contpar.newton_options.eigsolver is None, "bk_palc_run: no eigen-solve per step"
+    assert normC in (V.norm2, V.norminf), "bk_palc_run: normC is norm or norminf"
+    bls = alg.bls
+    assert isinstance(bls, (BorderingBLSB200, MatrixFreeBLSB200)), "bk_palc_run: bls must be one of the library's bordered solvers"
+    ls = contpar.newton_options.linsolver
+    bord = isinstance(bls, BorderingBLSB200)
+    po = _l.PalcOpts(ds=contpar.ds, dsmin=contpar.dsmin, dsmax=contpar.dsmax, a=contpar.a, p_min=contpar.p_min, p_max=contpar.p_max,
+                     theta=alg.theta, eta=contpar.eta, newton_tol=contpar.newton_options.tol, fd_eps=prob.delta,
+                     bls_tol=bls.tol if bord else 0.0, max_steps=contpar.max_steps, newton_maxit=contpar.newton_options.max_iterations,
+                     lens=prob.lens, tangent=0 if alg.tangent == "secant" else 1, bls=1 if bord else 0,
+                     bls_check_precision=int(bls.check_precision) if bord else 0, bls_k=bls.k if bord else 1,
+                     normc=1 if normC is V.norminf else 0)
+    go = (bls.solver or ls).opts()  # PALC hands the Newton linear solver to a bordered solver built without one (Palc.jl:100-110)
+    go_newton = ls.opts()
+    assert bytes(go) == bytes(go_newton), "bk_palc_run: one linear solver for the start-up Newton solves and the bordered solver"
+    ctx.set_params(prob.params)
+    max_rows = max_rows or contpar.max_steps + 8
+    rows = np.zeros((max_rows, _l.BK_PALC_ROW))
+    res = _l.PalcResult()
+    uf = DeviceVec(ctx, ctx.N)
+    as_row = lambda r: dict(param=r[0], x=r[1], itnewton=int(r[2]), itlinear=int(r[3]), ds=r[4], step=int(r[5]), n_unstable=-1)
+
+    def thunk(user, step, row, z_u, z_p):
+        r = np.ctypeslib.as_array(row, shape=(_l.BK_PALC_ROW,))
+        return 0 if callback(step, as_row(r), z_u, z_p) is False else 1
+
+    cb = _l.PalcCallback(thunk) if callback is not None else _l.PalcCallback()  # no-argument form = NULL
+    st = ctx.lib.bk_palc_run(ctx.handle, C.byref(po), C.byref(go), _l.ptr(prob.u0), float(prob.p0), _l.ptr(u1),
+                             0.0 if p1 is None else float(p1), rows.ctypes.data_as(C.POINTER(C.c_double)), max_rows, cb, None,
+                             uf.dptr, C.byref(res))
+    if st == -3:  # BK_ERR_STATE: the reference throws here (src/Continuation.jl:375-393)
+        raise RuntimeError("bk_palc_run: " + ctx.lib.bk_last_error(ctx.handle).decode())
+    _chk(ctx, st)
+    info = dict(steps=res.steps, nfail=res.nfail, stopped=res.stopped, work_newton=res.work_newton, work_linear=res.work_linear,
+                p=res.p_final, ds=res.ds_final, u=uf)
+    return [as_row(r) for r in rows[: res.nrows]], info

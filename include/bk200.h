@@ -186,6 +186,46 @@ int32_t bk_hessenberg_eig(const double* H, int32_t n, int32_t ldh, double* wr, d
  *   (BK_POTRAP_CGL2D contexts; x = [x_1..x_M; T], src/periodicorbit/PeriodicOrbitTrapeze.jl:249-330) */
 int32_t bk_potrap_set_section(bk_ctx* ctx, const double* phi, const double* xpi); /* length N-1 each */
 
+/* ---- the all-native PALC loop (optional entry): continuation(prob, PALC(...), opts; normC) of
+ *   src/Continuation.jl:349-504, 506-601 for the context's problem -- two start-up Newton solves (src/Newton.jl:66-114), secant or
+ *   Bordered tangent (src/continuation/Tangents.jl:8-42, 71-104), newton_palc corrector (src/continuation/Palc.jl:187-305,
+ *   linesearch = false) on bk_bls_matrixfree / bk_bls_bordering, step-size control (src/continuation/Contbase.jl:77-102) -- as host
+ *   C++ inside the library (csrc/bk_palc_loop.hpp), the state device-resident, one ABI crossing per BRANCH instead of a dozen per
+ *   Newton iteration.  It issues exactly the kernel sequence of the plugin-surface loop (julia/BK200.jl under continuation(...), or
+ *   bifurcationkit.jl_b200/palc.py), so the branch is bit-identical to that loop's.  detect_bifurcation = 0 (no eigen-solve per
+ *   step; call bk_eigs_shift_invert from the callback if wanted). */
+typedef struct bk_palc_opts {
+  double ds, dsmin, dsmax, a, p_min, p_max;  /* ContinuationPar (src/ContParameters.jl:44-100) */
+  double theta;                              /* PALC.theta (src/continuation/Palc.jl:70-84) */
+  double eta;                                /* second start point at p0 + ds / eta (src/Continuation.jl:384) */
+  double newton_tol;                         /* NewtonPar.tol */
+  double fd_eps;                             /* finite-difference step of dF/dp (Palc.jl:239-240); 0: sqrt(eps) */
+  double bls_tol;                            /* BorderingBLS.tol (check_precision) */
+  int32_t max_steps, newton_maxit;
+  int32_t lens;                              /* index of the continuation parameter in the context's parameter tuple */
+  int32_t tangent;                           /* 0 secant, 1 Bordered() */
+  int32_t bls;                               /* 0 MatrixFreeBLS, 1 BorderingBLS */
+  int32_t bls_check_precision, bls_k;        /* BorderingBLS fields (src/LinearBorderSolver.jl:59-75) */
+  int32_t normc;                             /* normC of the Newton residuals: 0 norm (2-norm), 1 norminf */
+} bk_palc_opts;
+enum { BK_PALC_ROW = 6 };                    /* doubles per row: param, ||u|| (record_from_solution), itnewton, itlinear, ds, step */
+typedef struct bk_palc_result {
+  int32_t nrows, steps, nfail;               /* rows written, accepted steps, rejected steps */
+  int32_t stopped;                           /* 0 max_steps / parameter bound, 1 ds fell to dsmin, 2 callback, 3 row buffer full */
+  int64_t work_newton, work_linear;          /* all corrector iterations, rejected attempts included */
+  double p_final, ds_final;
+} bk_palc_result;
+/* called at step 0 and after every accepted step (finalise_solution / callback of the reference); z_u is the DEVICE state;
+ * return 0 to stop the run */
+typedef int32_t (*bk_palc_callback)(void* user, int32_t step, const double* row, const double* z_u, double z_p);
+/* u0: start guess at p0 = params[lens] given by p0 (host or device, N doubles).  u1 != NULL: start from the two points (u0, p0),
+ * (u1, p1) without Newton corrections (iterate_from_two_points, src/Continuation.jl:408-456).  rows: HOST array, max_rows x
+ * BK_PALC_ROW.  u_final (may be NULL): last state, host or device.  Returns BK_ERR_STATE when a start-up Newton solve fails
+ * (the reference throws there, src/Continuation.jl:375-393). */
+int32_t bk_palc_run(bk_ctx* ctx, const bk_palc_opts* opts, const bk_gmres_opts* linsolver, const double* u0, double p0,
+                    const double* u1, double p1, double* rows, int32_t max_rows, bk_palc_callback cb, void* user,
+                    double* u_final, bk_palc_result* result);
+
 /* ---- environment switches read once by the library (tuning / diagnostics; none is needed for normal use)
  *   BK2_E=1..8          tile height of the TMA-ring Arnoldi kernels instead of the heuristic (bk_krylov.cu::plan2)
  *   BK_NO_PDL=1         launch without programmatic dependent launch (plain stream order)

@@ -268,4 +268,45 @@ function (e::ShiftInvertB200)(J::Jac, nev; kwargs...)
     return complex.(re, im_), vecs, nconv[] >= nev, Int(nops[])
 end
 
+# ---- the all-native loop (optional): one ccall per BRANCH instead of a dozen per Newton iteration ------------------------
+# bk_palc_run (include/bk200.h) runs continuation(prob, PALC(tangent, bls), opts; normC) of src/Continuation.jl:349-601 for the
+# context's own problem inside the library (csrc/bk_palc_loop.hpp): same kernels in the same order as the plugin-surface
+# path above, hence the same branch bit for bit.  Use it when no Julia callback is needed between the steps
+# (detect_bifurcation = 0); everything else keeps going through continuation(...).
+struct PalcOpts             # == bk_palc_opts
+    ds::Cdouble; dsmin::Cdouble; dsmax::Cdouble; a::Cdouble; p_min::Cdouble; p_max::Cdouble
+    theta::Cdouble; eta::Cdouble; newton_tol::Cdouble; fd_eps::Cdouble; bls_tol::Cdouble
+    max_steps::Int32; newton_maxit::Int32; lens::Int32; tangent::Int32; bls::Int32
+    bls_check_precision::Int32; bls_k::Int32; normc::Int32
+end
+struct PalcResult           # == bk_palc_result
+    nrows::Int32; steps::Int32; nfail::Int32; stopped::Int32
+    work_newton::Int64; work_linear::Int64; p_final::Cdouble; ds_final::Cdouble
+end
+"""
+    continuation_native(ctx, u0, params, lens::Int, alg::PALC, opts::ContinuationPar; normC = norm, u1 = nothing, p1 = 0.0)
+
+`lens` = 1-based index of the continuation parameter inside `params`.  `alg.bls` is a `BorderingBLSB200` or a `MatrixFreeBLSB200`,
+`opts.newton_options.linsolver` a `GMRESB200`.  Returns `(rows, result)`: `rows[:, k] = (param, ‖u‖, itnewton, itlinear, ds, step)`
+like `br.branch` (src/Continuation.jl:259-272), `result::PalcResult`, and the last state in a `DeviceVec`.
+"""
+function continuation_native(c::Context, u0, params, lens::Int, alg, opts; normC = norm, u1 = nothing, p1 = 0.0)
+    setparams!(c, params)
+    ls = opts.newton_options.linsolver
+    b = alg.bls
+    bord = b isa BorderingBLSB200
+    po = Ref(PalcOpts(opts.ds, opts.dsmin, opts.dsmax, opts.a, opts.p_min, opts.p_max, alg.θ, opts.η, opts.newton_options.tol, 0.0,
+                      bord ? b.tol : 0.0, opts.max_steps, opts.newton_options.max_iterations, lens - 1,
+                      alg.tangent isa BK.Bordered ? 1 : 0, bord ? 1 : 0, bord && b.check_precision ? 1 : 0, bord ? b.k : 1,
+                      normC === BK.norminf ? 1 : 0))
+    o = Ref(opts(ls))
+    maxrows = opts.max_steps + 8
+    rows = zeros(6, maxrows); res = Ref(PalcResult(0, 0, 0, 0, 0, 0, 0.0, 0.0)); uf = DeviceVec(c, c.N)
+    st = GC.@preserve u0 u1 ccall((:bk_palc_run, lib), Int32,
+        (Ptr{Cvoid}, Ptr{PalcOpts}, Ptr{GmresOpts}, Ptr{Float64}, Float64, Ptr{Float64}, Float64, Ptr{Float64}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{PalcResult}),
+        c.handle, po, o, ptr(u0), Float64(params[lens]), isnothing(u1) ? Ptr{Float64}(C_NULL) : ptr(u1), p1, rows, maxrows, C_NULL, C_NULL, uf.ptr, res)
+    check(c, st)   # BK_ERR_STATE: "Newton failed to converge for the initial guess" (src/Continuation.jl:375-393)
+    return rows[:, 1:res[].nrows], res[], uf
+end
+
 end # module

@@ -153,7 +153,7 @@ def step_size_control(ds, converged, itnewton, contpar):
     else:
         Nmax = contpar.newton_options.max_iterations
         factor = (Nmax - itnewton) / Nmax
-        dsnew = ds * (1 + contpar.a * factor**2)
+        dsnew = ds * (1 + contpar.a * (factor * factor))  # factor^2 is a literal power in Julia: x * x
     dsnew = np.sign(dsnew) * min(max(abs(dsnew), contpar.dsmin), contpar.dsmax)  # clamp_ds ContParameters.jl:107
     return float(dsnew), False
 
