@@ -47,11 +47,16 @@ class FoldSolution:
 class FoldMinAug:
     """[F(x, p); sigma(x, p)] with sigma from  [J a; b' 0] [v; sigma] = [0; 1]  (Govaerts 2000: a ~ left, b ~ right null vector)."""
 
-    def __init__(self, prob, a, b, bls, symmetric=True):
-        assert symmetric, "the adjoint Jacobian is not built: only self-adjoint problems (J' = J)"
-        self.prob, self.a, self.b, self.bls = prob, V.copy(a), V.copy(b), bls
+    def __init__(self, prob, a, b, bls, symmetric=True, norm=V.norm2):
+        assert symmetric or hasattr(prob, "Jt"), "non-symmetric problem: prob.Jt(x, p) (jacobian_adjoint) is required"
+        self.prob, self.a, self.b, self.bls, self.symmetric, self.norm = prob, V.copy(a), V.copy(b), bls, symmetric, norm
         self.zero = V.zeros_like(a)
         self.itlinear = 0
+        self.BT, self.CP = 1.0, 1.0  # test functions of the Bogdanov-Takens / cusp events (MinAugFold.jl:421-423, 551-575)
+
+    def _Jt(self, x, p):
+        """jacobian_adjoint(prob, x, p) (has_adjoint) -- J itself for a self-adjoint problem (is_symmetric, MinAugFold.jl:96-100)"""
+        return self.prob.J(x, p) if self.symmetric else self.prob.Jt(x, p)
 
     def _border(self, J, a, b):
         """linbdsolver(J, a, b, 0, zero, 1) -> (v, sigma): J v + a sigma = 0, <b, v> = 1"""
@@ -69,7 +74,7 @@ class FoldMinAug:
         eps = prob.delta
         J = prob.J(x, p)
         v, _ = self._border(J, self.a, self.b)
-        w, _ = self._border(J, self.b, self.a)          # adjoint system with J' = J
+        w, _ = self._border(J if self.symmetric else self._Jt(x, p), self.b, self.a)   # adjoint system J' w + b sigma2 = 0, <a, w> = 1
         # d_p F and sigma_p = -<w, d_p(J v)> by centred differences (MinAugFold.jl:92-101)
         dpF = prob.F(x, p + eps)
         V.axpby(dpF, -1.0 / (2 * eps), prob.F(x, p - eps), 1.0 / (2 * eps))
@@ -79,27 +84,46 @@ class FoldMinAug:
         sigma_p = -V.dot(w, jp)
         return v, w, dpF, sigma_p
 
-    def solve(self, x, p, rhsu, rhsp):
+    def solve(self, x, p, rhsu, rhsp, cache=None):
         """foldMALinearSolver: [J d_pF; sigma_x' sigma_p] [dX; dp] = [rhsu; rhsp] with
-        sigma_x = (J'(x) w - J'(x + eps v) w) / eps  (MinAugFold.jl:135-141)"""
+        sigma_x = (J'(x) w - J'(x + eps v) w) / eps  (MinAugFold.jl:135-141).  `cache`: an object whose `.terms` keeps
+        (d_pF, sigma_x, sigma_p) between the right-hand sides solved at the same (x, p)."""
         prob = self.prob
         eps = prob.delta
-        v, w, dpF, sigma_p = self.bordered_terms(x, p)
-        xs = V.copy(x)
-        V.axpby(xs, eps, v, 1.0)
-        u1 = _apply(prob.J(xs, p), w)
+        if cache is not None and cache.terms is not None:
+            dpF, sigma_x, sigma_p = cache.terms
+        else:
+            v, w, dpF, sigma_p = self.bordered_terms(x, p)
+            xs = V.copy(x)
+            V.axpby(xs, eps, v, 1.0)
+            u1 = _apply(self._Jt(xs, p), w)
+            sigma_x = _apply(self._Jt(x, p), w)
+            V.axpby(sigma_x, -1.0 / eps, u1, 1.0 / eps)  # (u2 - u1) / eps
+            if cache is not None:
+                cache.terms = (dpF, sigma_x, sigma_p)
         J = prob.J(x, p)                                 # back to the linearisation at x (one state per context)
-        sigma_x = _apply(J, w)
-        V.axpby(sigma_x, -1.0 / eps, u1, 1.0 / eps)      # (u2 - u1) / eps
         dX, dp, cv, it = self.bls(J, dpF, sigma_x, sigma_p, rhsu, rhsp)
         self.itlinear += int(np.sum(it))
         return dX, dp, cv
 
+    def update(self, x, p):
+        """update!(probma, iter, state) (MinAugFold.jl:276-309) and test_bt_cusp (:551-575): after an accepted step the border
+        vectors follow the null vectors, a <- w / ||w||, b <- v / ||v||; BT = <w / ||w||, v / ||v||>"""
+        J = self.prob.J(x, p)
+        v, _ = self._border(J, self.a, self.b)
+        w, _ = self._border(J if self.symmetric else self._Jt(x, p), self.b, self.a)
+        V.scale(v, 1.0 / self.norm(v))
+        V.scale(w, 1.0 / self.norm(w))
+        V.copyto(self.a, w)
+        V.copyto(self.b, v)
+        self.BT = V.dot(w, v)
+        return self.BT
 
-def newton_fold(prob, x0, p0, eigenvec, eigenvec_ad, opts, bls, normN=V.norm2):
+
+def newton_fold(prob, x0, p0, eigenvec, eigenvec_ad, opts, bls, normN=V.norm2, symmetric=True):
     """Newton on the MA system from the guess (x0, p0) with guesses for the right / left null vectors
     (newton_fold, MinAugFold.jl:201-222 + src/Newton.jl:66-114 on the bordered state)."""
-    ma = FoldMinAug(prob, eigenvec_ad, eigenvec, bls)
+    ma = FoldMinAug(prob, eigenvec_ad, eigenvec, bls, symmetric=symmetric)
     x, p = V.copy(x0), float(p0)
     F, sigma = ma.residual(x, p)
     res = math.hypot(normN(F), abs(sigma))
@@ -114,6 +138,167 @@ def newton_fold(prob, x0, p0, eigenvec, eigenvec_ad, opts, bls, normN=V.norm2):
         residuals.append(res)
         step += 1
     return FoldSolution(x, p, residuals, residuals[-1] < opts.tol, step, ma.itlinear, sigma)
+
+
+# ------------------------------------------------------------------------------------------------ Fold curves in two parameters
+class BorderedVec:
+    """BorderedArray(u, p) (src/BorderedArrays.jl:23-70, 86-217) with the method set of a DeviceVec, so that the PALC host
+    loop (palc.py) runs on the state of a minimally augmented problem unchanged: (x, p1) for Folds, (x, [p1, omega]) for Hopf
+    points (hopf_point, MinAugHopf.jl:13).  u is a DeviceVec or an ndarray, p a float or a short ndarray."""
+
+    def __init__(self, u, p):
+        self.u = u
+        self.p = float(p) if np.ndim(p) == 0 else np.array(p, dtype=np.float64)
+
+    def __len__(self):                 # Base.length(b) = length(b.u) + length(b.p)   (:49-50)
+        return len(self.u) + int(np.size(self.p))
+
+    def copy(self):
+        return BorderedVec(V.copy(self.u), self.p)
+
+    def copyto(self, src):
+        V.copyto(self.u, src.u)
+        self.p = src.p if np.ndim(src.p) == 0 else src.p.copy()
+        return self
+
+    def zero_(self):
+        V.scale(self.u, 0.0)
+        self.p = self.p * 0.0
+        return self
+
+    def scale_(self, a):
+        V.scale(self.u, a)
+        self.p = self.p * a
+        return self
+
+    def axpby_(self, a, x, b=1.0):     # VI.add!(y, x, a, b)
+        V.axpby(self.u, a, x.u, b)
+        self.p = a * x.p + b * self.p
+        return self
+
+    def dot(self, y):                  # VI.inner(a, b) = inner(a.u, b.u) + inner(a.p, b.p)   (:53)
+        return V.dot(self.u, y.u) + float(np.sum(self.p * y.p))
+
+    def norm(self):                    # :55-58
+        return math.sqrt(V.norm2(self.u) ** 2 + float(np.sum(self.p * self.p)))
+
+    def norminf(self):                 # :62
+        from .palc import nanmax2
+        return nanmax2(V.norminf(self.u), float(np.max(np.abs(self.p))))
+
+    def diffdot(self, x0, tau):
+        return V.diffdot(self.u, x0.u, tau.u) + float(np.sum((self.p - x0.p) * tau.p))
+
+
+class _FoldMAJacobian:
+    """jacobian(FoldMAProblem{MinAug}, z, p2): a handle on (x, p1, p2); the bordered terms are computed once per handle and
+    shared by the right-hand sides BorderingBLS solves with it (the reference recomputes them per right-hand side)."""
+
+    def __init__(self, pb, z, p2):
+        self.pb, self.z, self.p2, self.terms = pb, z, p2, None
+
+
+class FoldLinearSolverMinAug:
+    """(foldl::FoldLinearSolverMinAug)(Jfold, rhs) -> (sol, converged, iters)   (MinAugFold.jl:148-163)"""
+
+    def __call__(self, Jma, rhs):
+        pb, ma = Jma.pb, Jma.pb.ma
+        pb._set2(Jma.p2)
+        it0 = ma.itlinear
+        dX, dp, cv = ma.solve(Jma.z.u, Jma.z.p, rhs.u, rhs.p, cache=Jma)
+        return BorderedVec(dX, dp), cv, ma.itlinear - it0
+
+
+class FoldMAProblem:
+    """FoldMAProblem: the minimally augmented Fold system [F(x, p1, p2); sigma(x, p1, p2)] as a problem in the state
+    z = (x, p1) with continuation parameter p2 = params[lens2] (continuation_fold, MinAugFold.jl:366-452)."""
+
+    def __init__(self, ma, lens2, z0, record=None):
+        assert lens2 != ma.prob.lens, "Please choose 2 different parameters."
+        self.ma, self.lens2, self.u0 = ma, lens2, z0
+        self.p0 = float(ma.prob.params[lens2])
+        self.delta = ma.prob.delta
+        self.record = record or (lambda z: z.p)   # record_from_solution of the Fold curve: (p1, p2) -- p2 is the row's param
+
+    def _set2(self, p2):
+        self.ma.prob.params[self.lens2] = p2
+
+    def F(self, z, p2, out=None):
+        self._set2(p2)
+        Fu, sigma = self.ma.residual(z.u, z.p)
+        if out is None:
+            return BorderedVec(Fu, sigma)
+        V.copyto(out.u, Fu)
+        out.p = sigma
+        return out
+
+    def J(self, z, p2):
+        return _FoldMAJacobian(self, z, p2)
+
+
+class BorderingBLSHost:
+    """BorderingBLS with check_precision = false (BEC, src/LinearBorderSolver.jl:125-144) over ANY linear solver and any vectors
+    of the V interface: the `linear_algo` continuation_fold hands to PALC (MinAugFold.jl:446)."""
+
+    def __init__(self, solver):
+        self.solver = solver
+
+    def __call__(self, J, dR, dzu, dzp, R, n, xiu=1.0, xip=1.0, shift=None, dotscale=1.0):
+        assert shift is None
+        x1, cv1, it1 = self.solver(J, R)
+        dx, cv2, it2 = self.solver(J, dR)
+        dl = (n - dotscale * V.dot(dzu, x1) * xiu) / (dzp * xip - dotscale * V.dot(dzu, dx) * xiu)
+        V.axpby(x1, -dl, dx, 1.0)
+        return x1, dl, bool(cv1 and cv2), (it1, it2)
+
+
+@dataclass
+class FoldCurve:
+    rows: list      # palc rows: param = p2, x = record (default p1), itnewton, itlinear, ds, step
+    p1: list        # the Fold curve (p1[k], p2[k])
+    p2: list
+    BT: list        # test function <w / ||w||, v / ||v||> at every point: zero at a Bogdanov-Takens point (test_bt_cusp)
+    CP: list        # p1-component of the tangent: zero at a cusp
+    ma: object
+    state: object
+
+
+def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls, alg=None, normC=V.norminf, symmetric=True,
+                      update_minaug_every_step=1, record=None, callback=None):
+    """Codim-2 continuation of a Fold point in the parameters (p1 = params[prob.lens], p2 = params[lens2]):
+    continuation_fold(prob, alg, foldpointguess, par, lens1, lens2, eigenvec, eigenvec_ad, options_cont; jacobian_ma = MinAug())
+    (MinAugFold.jl:366-452).  PALC on the minimally augmented system, Newton linear solver = FoldLinearSolverMinAug over the
+    bordered solver `bls` (bdlinsolver: MatrixFreeBLSB200 / BorderingBLSB200 on the device), outer bordered solver =
+    BorderingBLS(that solver, check_precision = false), border vectors updated after every accepted step (update!), the
+    Bogdanov-Takens and cusp test functions recorded along the curve."""
+    from . import palc as P
+    ma = FoldMinAug(prob, eigenvec_ad, eigenvec, bls, symmetric=symmetric, norm=normC)
+    z0 = BorderedVec(V.copy(x0), p1_0)
+    pb = FoldMAProblem(ma, lens2, z0, record)
+    fls = FoldLinearSolverMinAug()
+    no = contpar.newton_options
+    cp = P.ContinuationPar(**{**contpar.__dict__, "newton_options": P.NewtonPar(tol=no.tol, max_iterations=no.max_iterations, linsolver=fls),
+                              "detect_bifurcation": 0})
+    alg = alg or P.PALC()
+    alg = P.PALC(tangent=alg.tangent, theta=alg.theta, bls=BorderingBLSHost(fls))
+    curve = FoldCurve([], [], [], [], [], ma, None)
+
+    def cb(st):
+        pb._set2(st.z_p)
+        if st.step % update_minaug_every_step == 0:
+            ma.update(st.z_u.u, st.z_u.p)
+        curve.p1.append(st.z_u.p)
+        curve.p2.append(st.z_p)
+        curve.BT.append(ma.BT)
+        curve.CP.append(st.tau_u.p)
+        return True if callback is None else callback(st)
+
+    p2_0 = prob.params[lens2]
+    try:
+        curve.rows, curve.state = P.continuation(pb, alg, cp, normC=normC, callback=cb)
+    finally:
+        prob.params[lens2] = p2_0  # the caller's parameter tuple is left as it was
+    return curve
 
 
 # ------------------------------------------------------------------------------------------------ Hopf
@@ -230,3 +415,104 @@ def newton_hopf(prob, cprob, x0, p0, omega0, eigenvec, eigenvec_ad, opts, ls, cl
         residuals.append(res)
         step += 1
     return HopfSolution(x, p, om, residuals, residuals[-1] < opts.tol, step, ma.itlinear)
+
+
+# ------------------------------------------------------------------------------------------------ Hopf curves in two parameters
+class _HopfMAJacobian:
+    def __init__(self, pb, z, p2):
+        self.pb, self.z, self.p2 = pb, z, p2
+
+
+class HopfLinearSolverMinAug:
+    """(hopfl::HopfLinearSolverMinAug)(Jhopf, rhs) -> (sol, converged, iters)   (MinAugHopf.jl:190-205)"""
+
+    def __call__(self, Jma, rhs):
+        pb, ma = Jma.pb, Jma.pb.ma
+        pb._set2(Jma.p2)
+        it0 = ma.itlinear
+        z = Jma.z
+        dX, dp, dom, cv = ma.solve(z.u, float(z.p[0]), float(z.p[1]), V.copy(rhs.u), float(rhs.p[0]), float(rhs.p[1]))
+        return BorderedVec(dX, [dp, dom]), cv, ma.itlinear - it0
+
+
+class HopfMAProblem:
+    """HopfMAProblem: [F(x, p1, p2); Re sigma; Im sigma] in the state z = (x, [p1, omega]) with continuation parameter
+    p2 = params[lens2] (continuation_hopf, MinAugHopf.jl:425-522)."""
+
+    def __init__(self, ma, lens2, z0, record=None):
+        assert lens2 != ma.prob.lens, "Please choose 2 different parameters."
+        self.ma, self.lens2, self.u0 = ma, lens2, z0
+        self.p0 = float(ma.prob.params[lens2])
+        self.delta = ma.prob.delta
+        self.record = record or (lambda z: float(z.p[0]))
+
+    def _set2(self, p2):
+        self.ma.prob.params[self.lens2] = p2
+        self.ma.cprob.params[self.lens2] = p2
+
+    def F(self, z, p2, out=None):
+        self._set2(p2)
+        Fu, sr, si = self.ma.residual(z.u, float(z.p[0]), float(z.p[1]))
+        if out is None:
+            return BorderedVec(Fu, [sr, si])
+        V.copyto(out.u, Fu)
+        out.p = np.array([sr, si])
+        return out
+
+    def J(self, z, p2):
+        return _HopfMAJacobian(self, z, p2)
+
+
+@dataclass
+class HopfCurve:
+    rows: list
+    p1: list        # the Hopf curve (p1[k], p2[k]) with the frequency omega[k]
+    p2: list
+    omega: list
+    ma: object
+    state: object
+    stopped_at_bt: bool = False
+
+
+def continuation_hopf(prob, cprob, x0, p1_0, omega0, lens2, eigenvec, eigenvec_ad, contpar, ls, cls, alg=None, normC=V.norminf,
+                      update_minaug_every_step=1, record=None, callback=None):
+    """Codim-2 continuation of a Hopf point in (p1 = params[prob.lens], p2 = params[lens2]): continuation_hopf(prob, alg,
+    hopfpointguess, par, lens1, lens2, eigenvec, eigenvec_ad, options_cont; jacobian_ma = MinAug()) (MinAugHopf.jl:425-522).
+    PALC on the minimally augmented system in the state (x, [p1, omega]); Newton linear solver = HopfLinearSolverMinAug (one
+    two-right-hand-side real solve + four complex shifted solves on the BK_COMPLEX twin `cprob`), outer bordered solver =
+    BorderingBLS(that solver, check_precision = false); after every accepted step a <- w / ||w||, b <- v / ||v|| (update!,
+    :323-367); the curve stops where omega -> 0 (Bogdanov-Takens, |omega| < 100 Newton tol)."""
+    from . import palc as P
+    ma = HopfMinAug(prob, cprob, eigenvec_ad, eigenvec, ls, cls)
+    z0 = BorderedVec(V.copy(x0), [p1_0, omega0])
+    pb = HopfMAProblem(ma, lens2, z0, record)
+    hls = HopfLinearSolverMinAug()
+    no = contpar.newton_options
+    cp = P.ContinuationPar(**{**contpar.__dict__, "newton_options": P.NewtonPar(tol=no.tol, max_iterations=no.max_iterations, linsolver=hls),
+                              "detect_bifurcation": 0})
+    alg = alg or P.PALC()
+    alg = P.PALC(tangent=alg.tangent, theta=alg.theta, bls=BorderingBLSHost(hls))
+    curve = HopfCurve([], [], [], [], ma, None)
+    cnorm = lambda z: float(np.max(np.abs(z)))
+
+    def cb(st):
+        pb._set2(st.z_p)
+        x, p1, om = st.z_u.u, float(st.z_u.p[0]), float(st.z_u.p[1])
+        if st.step % update_minaug_every_step == 0:
+            v, _ = ma._border(cprob.J(x, p1), complex(0.0, -om), ma.a, ma.b)
+            w, _ = ma._border(cprob.J(x, p1, transpose=True), complex(0.0, om), ma.b, ma.a)
+            ma.a, ma.b = w / cnorm(w), v / cnorm(v)
+        curve.p1.append(p1)
+        curve.p2.append(st.z_p)
+        curve.omega.append(om)
+        if abs(om) < 100 * no.tol:  # the frequency is null: not a Hopf point any more, the curve ends on a Bogdanov-Takens point
+            curve.stopped_at_bt = True
+            return False
+        return True if callback is None else callback(st)
+
+    p2_0, c2_0 = prob.params[lens2], cprob.params[lens2]
+    try:
+        curve.rows, curve.state = P.continuation(pb, alg, cp, normC=normC, callback=cb)
+    finally:
+        prob.params[lens2], cprob.params[lens2] = p2_0, c2_0
+    return curve

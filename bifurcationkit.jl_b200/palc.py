@@ -21,13 +21,18 @@ from .core import DeviceVec
 SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # src/Problems.jl:69
 
 
+def _obj(x):
+    """vectors that carry their own method set (DeviceVec; codim2.BorderedVec = BorderedArray(u, p)) vs plain ndarrays"""
+    return not isinstance(x, np.ndarray)
+
+
 class V:
-    """VectorInterface subset (src/BorderedArrays.jl:86-217) for DeviceVec and ndarray."""
+    """VectorInterface subset (src/BorderedArrays.jl:86-217) for DeviceVec, BorderedVec and ndarray."""
     host_alloc = None  # optional n -> ndarray factory (e.g. Context.pinned_empty) for host-resident state
 
     @staticmethod
     def copy(x):
-        if isinstance(x, DeviceVec) or V.host_alloc is None:
+        if _obj(x) or V.host_alloc is None:
             return x.copy()
         y = V.host_alloc(len(x))
         y[...] = x
@@ -35,7 +40,7 @@ class V:
 
     @staticmethod
     def copyto(dst, src):
-        if isinstance(dst, DeviceVec):
+        if _obj(dst):
             dst.copyto(src)
         else:
             dst[...] = src
@@ -44,7 +49,7 @@ class V:
     @staticmethod
     def axpby(y, a, x, b=1.0):
         """y <- a x + b y (VI.add!)"""
-        if isinstance(y, DeviceVec):
+        if _obj(y):
             return y.axpby_(a, x, b)
         if b != 1.0:
             _blas.dscal(b, y)
@@ -54,20 +59,20 @@ class V:
     @staticmethod
     def scale(x, a):
         """x <- a x (VI.scale!)"""
-        if isinstance(x, DeviceVec):
+        if _obj(x):
             return x.scale_(a)
         _blas.dscal(a, x)
         return x
 
     @staticmethod
     def dot(x, y):
-        return x.dot(y) if isinstance(x, DeviceVec) else float(np.dot(x, y))
+        return x.dot(y) if _obj(x) else float(np.dot(x, y))
 
     _scratch = {}  # host path: one reusable buffer per vector length (an 8 MB temporary per call costs ~1 ms of page faults)
 
     @staticmethod
     def diffdot(x, x0, tau):
-        if isinstance(x, DeviceVec):
+        if _obj(x):
             return x.diffdot(x0, tau)
         buf = V._scratch.get(len(x))
         if buf is None:
@@ -76,17 +81,17 @@ class V:
 
     @staticmethod
     def norm2(x):
-        return x.norm() if isinstance(x, DeviceVec) else float(np.linalg.norm(x))
+        return x.norm() if _obj(x) else float(np.linalg.norm(x))
 
     @staticmethod
     def norminf(x):
-        if isinstance(x, DeviceVec):
+        if _obj(x):
             return x.norminf()  # NaN-propagating on the device (k_reduce MODE 1)
         return nanmax2(float(np.max(x)), -float(np.min(x)))  # = max|x|, no temporary; NaN if any entry is NaN
 
     @staticmethod
     def zeros_like(x):
-        if isinstance(x, DeviceVec):
+        if _obj(x):
             return x.copy().zero_()
         if V.host_alloc is None:
             return np.zeros_like(x)

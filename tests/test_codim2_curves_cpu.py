@@ -1,0 +1,315 @@
+"""CPU tests of the codim-2 host logic (bifurcationkit.jl_b200/codim2.py: continuation_fold / continuation_hopf) on
+host arrays with the oracle's dense solvers as the backend -- pinned to the reference's own golden values:
+test/fold_codim_2/codim2.jl (CO-oxidation model): the Fold point `sn.u.u`, `sn.u.p` (:66-69), the Bogdanov-Takens point on
+the Fold curve at k = 0.9716038596420551 (:88-90), and the null-vector checks of the updated border vectors (:93-106)."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from oracle import krylov, bls as obls
+from tests.test_host_logic_cpu import BlsAdapter
+
+
+class NumpyProblem2:
+    """Duck-typed BifurcationProblemB200 on host arrays with a parameter tuple and a lens (index): F(x, params), J(x, params)."""
+
+    def __init__(self, F, J, u0, params, lens, record=None):
+        self.F_, self.J_, self.u0, self.params, self.lens = F, J, u0, list(params), lens
+        self.p0 = float(params[lens])
+        self.delta = float(np.sqrt(np.finfo(float).eps))
+        self.record = record or (lambda x: float(np.linalg.norm(x)))
+
+    def _par(self, p):
+        q = list(self.params)
+        q[self.lens] = p
+        return q
+
+    def F(self, x, p, out=None):
+        r = self.F_(x, self._par(p))
+        if out is not None:
+            out[...] = r
+            return out
+        return r
+
+    def J(self, x, p):
+        return self.J_(x, self._par(p))
+
+    def Jt(self, x, p):  # jacobian_adjoint
+        return self.J_(x, self._par(p)).T
+
+
+def COm(u, q):
+    """test/fold_codim_2/codim2.jl:8-17"""
+    q1, q2, q3, q4, q5, q6, k = q
+    x, y, s = u
+    z = 1 - x - y - s
+    return np.array([2 * q1 * z**2 - 2 * q5 * x**2 - q3 * x * y, q2 * z - q6 * y - q3 * x * y, q4 * z - k * q4 * s])
+
+
+def COmJ(u, q):
+    q1, q2, q3, q4, q5, q6, k = q
+    x, y, s = u
+    z = 1 - x - y - s
+    return np.array([[-4 * q1 * z - 4 * q5 * x - q3 * y, -4 * q1 * z - q3 * x, -4 * q1 * z],
+                     [-q2 - q3 * y, -q2 - q6 - q3 * x, -q2],
+                     [-q4, -q4, -q4 - k * q4]])
+
+
+PAR_COM = [2.5, 2.0, 10.0, 0.0675, 1.0, 0.1, 0.4]          # (q1, q2, q3, q4, q5, q6, k), codim2.jl:20
+SN_U = np.array([0.05402941507127516, 0.3022414400400177, 0.45980653206336225])  # codim2.jl:67
+SN_P = 1.0522002878699546                                   # codim2.jl:68
+BT_K = 0.9716038596420551                                   # codim2.jl:90
+
+
+@pytest.fixture(scope="module")
+def com_fold():
+    """the branch of codim2.jl:22-30 in q2 (downwards from q2 = 2), its second turning point refined by newton_fold"""
+    bk = g.load_package()
+    P, C2 = bk.palc, bk.codim2
+    ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
+    prob = NumpyProblem2(COm, COmJ, np.array([0.07, 0.2, 5.0]), PAR_COM, 1)
+    cp = P.ContinuationPar(p_min=0.6, p_max=2.5, ds=-0.002, dsmax=0.01, dsmin=1e-4, max_steps=3000,
+                           newton_options=P.NewtonPar(tol=1e-10, max_iterations=25, linsolver=ls))
+    pts = []
+    rows, _ = P.continuation(prob, P.PALC(bls=bls), cp, normC=P.norminf,
+                             callback=lambda s: pts.append((s.z_u.copy(), s.z_p, s.tau_u.copy())) or True)
+    ps = [r["param"] for r in rows]
+    turns = [i for i in range(1, len(ps) - 1) if (ps[i] - ps[i - 1]) * (ps[i + 1] - ps[i]) < 0]
+    assert len(turns) == 2 and rows[-1]["param"] == 0.6   # the S-shaped branch of the CO model: two folds
+    x0, p0, tau = pts[turns[1]]
+    t = tau / np.linalg.norm(tau)
+    sol = C2.newton_fold(prob, x0, p0, t, t, P.NewtonPar(tol=1e-10, max_iterations=10, linsolver=ls), bls, symmetric=False)
+    return bk, prob, ls, bls, sol, t
+
+
+def test_fold_point_of_the_co_model_matches_the_reference(com_fold):
+    """codim2.jl:64-69: sn = newton(br, 3; bdlinsolver = MatrixBLS()) -> sn.u.u, sn.u.p (rtol 1e-4 there)"""
+    _, prob, _, _, sol, _ = com_fold
+    assert sol.converged and sol.itnewton <= 4
+    assert np.allclose(sol.u, SN_U, rtol=1e-9) and abs(sol.p - SN_P) < 1e-10
+    J = COmJ(sol.u, prob._par(sol.p))
+    assert np.min(np.abs(np.linalg.eigvals(J))) < 1e-9 and np.linalg.norm(COm(sol.u, prob._par(sol.p))) < 1e-12
+
+
+def test_fold_curve_of_the_co_model(com_fold):
+    """codim2.jl:75-106: continuation of the Fold in (q2, k), k from 0.4 to 1 in at most 50 steps: the Bogdanov-Takens point (zero
+    of the test function <a, b> of the updated border vectors; reported at k = 0.97160386 by the reference), a singular Jacobian
+    at the last point and a, b equal to the null vectors of J', J there."""
+    bk, prob, ls, bls, sol, t = com_fold
+    P, C2 = bk.palc, bk.codim2
+    cpf = P.ContinuationPar(p_min=0.0, p_max=1.0, ds=0.002, dsmax=0.01, dsmin=1e-4, max_steps=50,
+                            newton_options=P.NewtonPar(tol=1e-10, max_iterations=25, linsolver=ls))
+    curve = C2.continuation_fold(prob, sol.u, sol.p, 6, t, t, cpf, bls, symmetric=False, normC=P.norminf)
+    assert prob.params == PAR_COM                       # the caller's parameters are restored
+    assert curve.p2[0] == 0.4 and abs(curve.p1[0] - SN_P) < 1e-10 and curve.p2[-1] == 1.0 and len(curve.rows) <= 51
+    assert max(r["itnewton"] for r in curve.rows) <= 3  # Newton on the MA system converges quadratically from the predictor
+    # every point of the curve is a Fold point: F = 0 and a singular Jacobian
+    z = curve.state.z_u
+    par = list(PAR_COM)
+    par[1], par[6] = z.p, curve.state.z_p
+    Jl = COmJ(z.u, par)
+    ev, evec = np.linalg.eig(Jl)
+    i0 = int(np.argmin(np.abs(ev)))
+    assert abs(ev[i0]) < 1e-10 and np.linalg.norm(COm(z.u, par)) < 1e-9          # codim2.jl:96-98
+    zeta = evec[:, i0].real
+    b = curve.ma.b
+    assert np.allclose(b / np.linalg.norm(b), zeta * np.sign(zeta[0]) * np.sign(b[0]), atol=1e-7)   # :99-100
+    ev2, evec2 = np.linalg.eig(Jl.T)
+    zs = evec2[:, int(np.argmin(np.abs(ev2)))].real
+    a = curve.ma.a
+    assert np.allclose(a / np.linalg.norm(a), zs * np.sign(zs[0]) * np.sign(a[0]), atol=1e-7)       # :102-105
+    # Bogdanov-Takens: sign change of the test function; located by a second pass with small steps from the bracketing point
+    bt, k = np.array(curve.BT), np.array(curve.p2)
+    cross = [j for j in range(len(bt) - 1) if bt[j] * bt[j + 1] < 0]
+    assert len(cross) == 1
+    j = cross[0]
+    assert abs(k[j] + (k[j + 1] - k[j]) * bt[j] / (bt[j] - bt[j + 1]) - BT_K) < 1e-3
+    pts = []
+    C2.continuation_fold(prob, sol.u, sol.p, 6, t, t, cpf, bls, symmetric=False, normC=P.norminf,
+                         callback=lambda st: pts.append((st.z_u.u.copy(), st.z_u.p, st.z_p)) or True)
+    xs, q2s, ks = pts[j]
+    prob.params[6] = ks
+    fine = P.ContinuationPar(p_min=0.0, p_max=1.0, ds=2e-4, dsmax=2e-4, dsmin=1e-5, max_steps=40,
+                             newton_options=P.NewtonPar(tol=1e-11, max_iterations=25, linsolver=ls))
+    c2 = C2.continuation_fold(prob, xs, q2s, 6, curve.ma.b, curve.ma.a, fine, bls, symmetric=False, normC=P.norminf)
+    prob.params[6] = PAR_COM[6]
+    bt2, k2 = np.array(c2.BT), np.array(c2.p2)
+    jj = [i for i in range(len(bt2) - 1) if bt2[i] * bt2[i + 1] < 0]
+    assert len(jj) == 1
+    i = jj[0]
+    k_bt = k2[i] + (k2[i + 1] - k2[i]) * bt2[i] / (bt2[i] - bt2[i + 1])
+    # independent location: the Fold at fixed k by a dense root solve (F = 0, det J = 0), then the zero of <left, right null vector>
+    from scipy.optimize import brentq, fsolve
+
+    def wv(kk):
+        def H(zz):
+            q = list(PAR_COM)
+            q[1], q[6] = zz[3], kk
+            return np.concatenate([COm(zz[:3], q), [1e3 * np.linalg.det(COmJ(zz[:3], q))]])
+        zz = fsolve(H, np.array([xs[0], xs[1], xs[2], q2s]), xtol=1e-12)
+        q = list(PAR_COM)
+        q[1], q[6] = zz[3], kk
+        Jk = COmJ(zz[:3], q)
+        e1, v1 = np.linalg.eig(Jk)
+        e2, w1 = np.linalg.eig(Jk.T)
+        v, w = v1[:, np.argmin(np.abs(e1))].real, w1[:, np.argmin(np.abs(e2))].real
+        return (w * np.sign(w[2])) @ (v * np.sign(v[1]))
+    k_true = brentq(wv, 0.9712, 0.9716, xtol=1e-13)
+    assert abs(k_bt - k_true) < 1e-6, (k_bt, k_true)
+    # the reference's value (codim2.jl:90, pinned there at rtol 1e-5 across its own Jacobian variants) is the end point of its event
+    # bisection (n_inversion = 4 halvings of dsmax = 0.01 steps): it sits 2e-4 from the zero of the test function
+    assert abs(k_bt - BT_K) < 5e-4, k_bt
+
+
+def test_fold_curve_known_answer_cusp_family():
+    """F = r + s x - x^3: Folds at 3 x^2 = s, r = -2 x^3 -- the curve (r, s) = (-2 (s/3)^(3/2), s); continued in s from s = 1
+    upwards and downwards (towards the cusp at the origin, where the p1-component of the tangent vanishes)."""
+    bk = g.load_package()
+    P, C2 = bk.palc, bk.codim2
+    ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
+    F = lambda x, q: q[0] + q[1] * x - x**3
+    J = lambda x, q: np.diag(q[1] - 3 * x**2)
+    s0 = 1.0
+    x0 = np.array([np.sqrt(s0 / 3)])
+    prob = NumpyProblem2(F, J, x0 + 0.01, [-2 * x0[0] ** 3 + 0.01, s0], 0)
+    one = np.array([1.0])
+    sol = C2.newton_fold(prob, prob.u0, prob.p0, one, one, P.NewtonPar(tol=1e-12, max_iterations=10, linsolver=ls), bls)
+    assert sol.converged and abs(sol.u[0] - x0[0]) < 1e-8 and abs(sol.p + 2 * x0[0] ** 3) < 1e-8
+    for ds, smax, smin in ((0.01, 2.0, 0.0), (-0.01, 2.0, 0.05)):
+        cp = P.ContinuationPar(p_min=smin, p_max=smax, ds=ds, dsmax=0.05, dsmin=1e-4, max_steps=200,
+                               newton_options=P.NewtonPar(tol=1e-11, max_iterations=15, linsolver=ls))
+        curve = C2.continuation_fold(prob, sol.u, sol.p, 1, one, one, cp, bls, normC=P.norminf)
+        r, s = np.array(curve.p1), np.array(curve.p2)
+        assert s[-1] == (smax if ds > 0 else smin) and len(s) > 10
+        assert np.max(np.abs(r + 2 * (s / 3) ** 1.5)) < 1e-8
+        cpv = np.abs(np.array(curve.CP))
+        if ds < 0:
+            assert cpv[-1] < cpv[0]                      # dr/ds -> 0 towards the cusp
+
+
+def test_bordered_vec_algebra():
+    """BorderedArray semantics (src/BorderedArrays.jl:49-62, 86-217) of the MA state vector"""
+    bk = g.load_package()
+    BV, V = bk.codim2.BorderedVec, bk.palc.V
+    rng = np.random.default_rng(0)
+    a, b, c = (BV(rng.standard_normal(5), rng.standard_normal()) for _ in range(3))
+    cat = lambda z: np.concatenate([z.u, [z.p]])
+    assert len(a) == 6
+    assert np.isclose(V.dot(a, b), cat(a) @ cat(b)) and np.isclose(V.norm2(a), np.linalg.norm(cat(a)))
+    assert np.isclose(V.norminf(a), np.abs(cat(a)).max()) and np.isclose(V.diffdot(a, b, c), (cat(a) - cat(b)) @ cat(c))
+    y = V.copy(a)
+    V.axpby(y, 2.0, b, -0.5)
+    assert np.allclose(cat(y), 2 * cat(b) - 0.5 * cat(a))
+    V.scale(y, 3.0)
+    assert np.allclose(cat(y), 3 * (2 * cat(b) - 0.5 * cat(a)))
+    z = V.zeros_like(a)
+    assert np.all(cat(z) == 0) and np.all(cat(a) != 0)
+    V.copyto(z, b)
+    assert np.array_equal(cat(z), cat(b)) and z.u is not b.u
+    nan = BV(np.array([1.0, np.nan]), 0.0)
+    assert np.isnan(V.norminf(nan))
+
+
+# ------------------------------------------------------------------------------------------------ Hopf curves
+from tests.test_host_logic_cpu import DenseComplexProblem, _dense_cls, _dense_ls2  # noqa: E402
+
+
+class DenseComplexProblem2:
+    """complexified twin of a NumpyProblem2 (cprob of codim2.HopfMinAug): J(x, p, transpose) -> callable on complex vectors"""
+
+    def __init__(self, prob):
+        self.prob, self.params, self.lens = prob, prob.params, prob.lens  # the SAME parameter list: one problem, two views
+
+    def J(self, x, p, transpose=False):
+        M = np.asarray(self.prob.J(x, p), dtype=float)
+        return DenseComplexProblem.Jc(M.T.copy() if transpose else M)
+
+
+def test_hopf_curve_of_the_brusselator_is_analytic():
+    """x' = a - (b+1) x + x^2 y, y' = b x - x^2 y: Hopf points at b = 1 + a^2, omega = a, equilibrium (a, b / a) --
+    continuation_hopf in (b; a) from a = 1.3 up to a = 2 and down to a = 0.6 reproduces the curve"""
+    bk = g.load_package()
+    P, C2 = bk.palc, bk.codim2
+    F = lambda x, q: np.array([q[0] - (q[1] + 1) * x[0] + x[0] ** 2 * x[1], q[1] * x[0] - x[0] ** 2 * x[1]])
+    J = lambda x, q: np.array([[-(q[1] + 1) + 2 * x[0] * x[1], x[0] ** 2], [q[1] - 2 * x[0] * x[1], -x[0] ** 2]])
+    a0 = 1.3
+    b0 = 1 + a0 * a0
+    x0 = np.array([a0, b0 / a0])
+    prob = NumpyProblem2(F, J, x0, [a0, b0], 1)
+    cprob = DenseComplexProblem2(prob)
+    vals, vecs = np.linalg.eig(J(x0, [a0, b0]))
+    k = int(np.argmax(vals.imag))
+    valt, vect = np.linalg.eig(J(x0, [a0, b0]).T)
+    kt = int(np.argmin(valt.imag))
+    opts = P.NewtonPar(tol=1e-10, max_iterations=15, linsolver=krylov.DefaultLS())
+    for ds, amin, amax in ((0.01, 0.5, 2.0), (-0.01, 0.6, 2.5)):
+        cp = P.ContinuationPar(p_min=amin, p_max=amax, ds=ds, dsmax=0.05, dsmin=1e-4, max_steps=200, newton_options=opts)
+        curve = C2.continuation_hopf(prob, cprob, x0, b0, a0, 0, vecs[:, k], vect[:, kt], cp, _dense_ls2, _dense_cls)
+        a, b, om = np.array(curve.p2), np.array(curve.p1), np.array(curve.omega)
+        assert a[-1] == (amax if ds > 0 else amin) and len(a) > 10 and not curve.stopped_at_bt
+        assert np.max(np.abs(b - (1 + a * a))) < 1e-8 and np.max(np.abs(np.abs(om) - a)) < 1e-8
+        assert prob.params == [a0, b0]
+        xs = curve.state.z_u.u
+        assert np.allclose(xs, [a[-1], b[-1] / a[-1]], atol=1e-8)
+        assert max(r["itnewton"] for r in curve.rows) <= 4
+
+
+def test_hopf_curve_of_the_co_model_ends_on_the_bogdanov_takens_point(com_fold):
+    """test/fold_codim_2/codim2.jl:118-146 continues the Hopf point of the CO branch in (q2, k).  Towards larger k that curve
+    ends where its frequency vanishes -- on the Bogdanov-Takens point of the Fold curve (test_fold_curve_of_the_co_model:
+    the one at k = 0.7223 on the curve through the branch's first fold): two independent continuations (real bordered systems
+    there, complex shifted ones here) meet."""
+    bk, prob, ls, bls, sol, t = com_fold
+    P, C2 = bk.palc, bk.codim2
+    # a Hopf point on the q2-branch at k = 0.4: scan the branch for a complex pair crossing the imaginary axis
+    cp = P.ContinuationPar(p_min=0.6, p_max=2.5, ds=-0.002, dsmax=0.01, dsmin=1e-4, max_steps=3000,
+                           newton_options=P.NewtonPar(tol=1e-10, max_iterations=25, linsolver=ls))
+    pts = []
+    P.continuation(prob, P.PALC(bls=bls), cp, normC=P.norminf, callback=lambda s: pts.append((s.z_u.copy(), s.z_p)) or True)
+    lead = []
+    for x, p in pts:
+        ev = np.linalg.eigvals(COmJ(x, prob._par(p)))
+        c = ev[np.abs(ev.imag) > 1e-6]
+        lead.append(c.real.max() if len(c) else np.nan)
+    lead = np.array(lead)
+    idx = [i for i in range(len(lead) - 1) if np.isfinite(lead[i]) and np.isfinite(lead[i + 1]) and lead[i] * lead[i + 1] < 0]
+    assert idx, "no Hopf point on the branch"
+    x0, p0 = pts[idx[0]]
+    Jh = COmJ(x0, prob._par(p0))
+    vals, vecs = np.linalg.eig(Jh)
+    kk = int(np.argmax(vals.imag))
+    valt, vect = np.linalg.eig(Jh.T)
+    kt = int(np.argmin(valt.imag))
+    cprob = DenseComplexProblem2(prob)
+    opts = P.NewtonPar(tol=1e-10, max_iterations=15, linsolver=ls)
+    hp = C2.newton_hopf(prob, cprob, x0, p0, vals[kk].imag, vecs[:, kk], vect[:, kt], opts, _dense_ls2, _dense_cls)
+    assert hp.converged, hp.residuals
+    ev = np.linalg.eigvals(COmJ(hp.u, prob._par(hp.p)))
+    assert abs(ev[np.argmax(ev.imag)].real) < 1e-8 and abs(ev.imag.max() - abs(hp.omega)) < 1e-8   # codim2.jl:123-131
+    cph = P.ContinuationPar(p_min=0.0, p_max=1.0, ds=0.002, dsmax=0.01, dsmin=1e-6, max_steps=400, newton_options=opts)
+    curve = C2.continuation_hopf(prob, cprob, hp.u, hp.p, hp.omega, 6, vecs[:, kk], vect[:, kt], cph, _dense_ls2, _dense_cls)
+    om, k = np.abs(np.array(curve.omega)), np.array(curve.p2)
+    assert curve.stopped_at_bt and k[0] == 0.4 and om[-1] < 1e-8 and prob.params == PAR_COM
+    # omega^2 vanishes linearly at a Bogdanov-Takens point: extrapolate the last genuine Hopf points to omega = 0
+    m = np.where(om > 1e-3)[0][-4:]
+    k_hopf_end = np.polyval(np.polyfit(om[m] ** 2, k[m], 1), 0.0)
+    # the Fold curve through the FIRST fold of the branch (q2 = 1.0420) and the zero of its Bogdanov-Takens test function
+    pts2 = []
+    rows = P.continuation(prob, P.PALC(bls=bls), cp, normC=P.norminf, callback=lambda s: pts2.append((s.z_u.copy(), s.z_p, s.tau_u.copy())) or True)[0]
+    ps = [r["param"] for r in rows]
+    i1 = next(i for i in range(1, len(ps) - 1) if (ps[i] - ps[i - 1]) * (ps[i + 1] - ps[i]) < 0)
+    xf, pf, tau = pts2[i1]
+    tf = tau / np.linalg.norm(tau)
+    f1 = C2.newton_fold(prob, xf, pf, tf, tf, P.NewtonPar(tol=1e-10, max_iterations=10, linsolver=ls), bls, symmetric=False)
+    assert f1.converged and abs(f1.p - 1.042048505) < 1e-8
+    cpf = P.ContinuationPar(p_min=0.0, p_max=1.0, ds=0.002, dsmax=0.005, dsmin=1e-4, max_steps=200,
+                            newton_options=P.NewtonPar(tol=1e-10, max_iterations=25, linsolver=ls))
+    fc = C2.continuation_fold(prob, f1.u, f1.p, 6, tf, tf, cpf, bls, symmetric=False, normC=P.norminf)
+    bt, kf = np.array(fc.BT), np.array(fc.p2)
+    j = next(i for i in range(len(bt) - 1) if bt[i] * bt[i + 1] < 0)
+    k_bt = kf[j] + (kf[j + 1] - kf[j]) * bt[j] / (bt[j] - bt[j + 1])
+    assert 0.70 < k_bt < 0.74 and abs(k_hopf_end - k_bt) < 1e-3, (k_hopf_end, k_bt)
+    # ... and the (q2, k) of the two curves agree there as well
+    q2_hopf_end = np.polyval(np.polyfit(om[m] ** 2, np.array(curve.p1)[m], 1), 0.0)
+    q2_bt = fc.p1[j] + (fc.p1[j + 1] - fc.p1[j]) * bt[j] / (bt[j] - bt[j + 1])
+    assert abs(q2_hopf_end - q2_bt) < 1e-3, (q2_hopf_end, q2_bt)
