@@ -306,6 +306,11 @@ class StepTimer:
         self.ctx.sync()
         return float(sum(a.elapsed_time(b) for a, b in self.pairs))
 
+    def step_ms(self):
+        """device time of every closed pair, in order (call after total_ms): pair k = continuation step k + 1 with the rejected
+        attempts before it"""
+        return [float(a.elapsed_time(b)) for a, b in self.pairs]
+
 
 def make_algs(bk, ctx, ls, n):
     """(fine alg, fine ContinuationPar factory, scout alg, scout ContinuationPar)"""
@@ -360,6 +365,10 @@ def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timi
             rows, st = [], None
     ms = tm.total_ms()
     ctx.sync()
+    try:
+        info["step_ms"] = tm.step_ms() if world == 1 else None
+    except Exception:  # informational only: never let it touch the measurement
+        info["step_ms"] = None
     torch.cuda.profiler.stop()
     ctx.set_timing(False)
     s1 = ctx.stats()
@@ -553,6 +562,19 @@ def main():
                "per_rank": per_rank, "scout_ms": info["scout_ms"], "scout_points": info["scout_points"],
                "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())] if nst else None}),
            "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline, "e2e": e2e}
+
+    # ---- the GPU arm on the reference arm's sample: `--impl reference` times the first ref_batches batches of the window (a bounded
+    # sample, cheaper per step than the window's average: the Krylov counts grow along the branch), `value` the whole window
+    try:
+        sm = info.get("step_ms")
+        nref = max(1, min(K, args.ref_batches)) * B
+        if sm and len(sm) >= nref:
+            out["details"]["per_batch_ms"] = [round(float(sum(sm[i * B:(i + 1) * B])), 1) for i in range(K)]
+            out["details"]["on_reference_sample"] = {
+                "steps": nref, "steps_per_s": (world if replicas else 1) * nref / (sum(sm[:nref]) * 1e-3),
+                "note": f"this rank's device time over the first {nref} continuation steps of the window = the sample bench.py --impl reference times"}
+    except Exception as exc:  # informational only
+        out["details"]["on_reference_sample"] = {"error": repr(exc)}
 
     # ---- cpu_baseline: C++/OpenMP restatement on the host cores, bounded sample from the same start point
     if not args.no_cpu_baseline and world == 1:
