@@ -313,3 +313,31 @@ def test_hopf_curve_of_the_co_model_ends_on_the_bogdanov_takens_point(com_fold):
     q2_hopf_end = np.polyval(np.polyfit(om[m] ** 2, np.array(curve.p1)[m], 1), 0.0)
     q2_bt = fc.p1[j] + (fc.p1[j + 1] - fc.p1[j]) * bt[j] / (bt[j] - bt[j + 1])
     assert abs(q2_hopf_end - q2_bt) < 1e-3, (q2_hopf_end, q2_bt)
+
+
+@pytest.mark.parametrize("vector_p", [False, True])
+def test_bordered_vec_reference_cases(vector_p):
+    """test/linear_solvers/bordered_arrays.jl:17-60 (x = BorderedArray([1, 2], 3), y = BorderedArray([4, 5], 6), scalar and
+    one-element-vector p): zerovector, scale, add!, inner on the concatenated entries; test_linear.jl:13-34: length == 11"""
+    bk = g.load_package()
+    BV, V = bk.codim2.BorderedVec, bk.palc.V
+    mk = lambda u, p: BV(np.array(u, dtype=float), np.array([p]) if vector_p else p)
+    cat = lambda z: np.concatenate([z.u, np.atleast_1d(z.p)])
+    x, y = mk([1.0, 2.0], 3.0), mk([4.0, 5.0], 6.0)
+    z = V.zeros_like(x)
+    assert np.all(cat(z) == 0.0) and np.array_equal(cat(x), [1, 2, 3])           # zerovector leaves x alone
+    alpha = -0.7364
+    xs = V.copy(x)
+    V.scale(xs, alpha)
+    assert np.allclose(cat(xs), alpha * cat(x)) and np.array_equal(cat(x), [1, 2, 3])
+    ya = V.copy(y)
+    V.axpby(ya, 2.0 / 3, x, 1.0)                                                   # VI.add!(y, x, 2/3, 1)
+    assert np.allclose(cat(ya), cat(y) + 2.0 / 3 * cat(x)) and np.array_equal(cat(x), [1, 2, 3])
+    assert V.dot(x, y) == 1 * 4 + 2 * 5 + 3 * 6 and len(x) == 3
+    assert len(BV(np.random.default_rng(0).random(10), 1.0)) == 11
+    c = V.copy(x)
+    V.scale(c, 2.0)
+    assert np.array_equal(cat(x), [1, 2, 3])                                       # copies do not alias (neither u nor p)
+    V.copyto(c, y)
+    V.scale(c, 2.0)
+    assert np.array_equal(cat(y), [4, 5, 6])
