@@ -246,3 +246,53 @@ def curve_distance(branch, ref):
             d = min(d, float(np.linalg.norm(p - (q0 + t * v))))
         worst = max(worst, d)
     return worst
+
+
+# ======================================================================================================================
+# bothside = true: the one split of a continuation job the reference itself offers (src/Continuation.jl:687-700): two
+# independent iterators from the same start point, ds and -ds, merged by _merge (src/Results.jl:464-489).  On two GPUs each
+# direction runs on its own device (replicated start state, nothing crosses NVLink), the rows are all_gathered and every rank
+# assembles the same branch.
+# ======================================================================================================================
+def merge_bothside(fwd, bwd, tol=1e-6):
+    """_merge(resfwd, resbwd): both runs start on the same point, so the merged branch is the backward run reversed followed
+    by the forward run (`_cat!(_reverse(br2), br1)`, src/Results.jl:476-478) -- the start point appears twice, as in the
+    reference -- with the steps renumbered along the merged branch.  fwd / bwd: (n, >= 2) arrays or lists of row dicts."""
+    arr = lambda rows: rows_to_array(rows, len(rows)) if len(rows) and isinstance(rows[0], dict) else np.asarray(rows, dtype=float)
+    f, b = arr(fwd), arr(bwd)
+    f, b = f[~np.isnan(f[:, 0])], b[~np.isnan(b[:, 0])]
+    if not len(b):
+        return f
+    if not len(f):
+        return b[::-1]
+    same = lambda r, s: max(abs(r[0] - s[0]), abs(r[1] - s[1])) < tol
+    if same(f[0], b[0]):
+        return np.concatenate([b[::-1], f])
+    if same(f[0], b[-1]):
+        return np.concatenate([b, f])
+    if same(f[-1], b[0]):
+        return np.concatenate([f, b])
+    return np.concatenate([f, b[::-1]])
+
+
+def continuation_bothside(P, make_prob, alg, contpar, normC, dist=None, torch=None, device="cpu", nrows=None):
+    """continuation(prob, alg, contpar; bothside = true).  make_prob() -> a fresh problem (the reference deep-copies the iterator:
+    some problems are changed in place).  Without `dist` (or world 1) both directions run here, one after the other; with a
+    process group of >= 2 ranks, rank 0 runs ds, rank 1 runs -ds (further ranks idle), the rows are all_gathered and merged on
+    every rank.  Returns (merged (n, 4) array of (param, x, itnewton, itlinear), this rank's own rows)."""
+    import copy
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+
+    def run(sign):
+        cp = copy.copy(contpar)
+        cp.ds = sign * contpar.ds
+        return P.continuation(make_prob(), alg, cp, normC=normC)[0]
+
+    if world == 1:
+        fwd, bwd = run(1.0), run(-1.0)
+        return merge_bothside(fwd, bwd), fwd + bwd
+    mine = run(1.0) if rank == 0 else (run(-1.0) if rank == 1 else [])
+    nrows = nrows or contpar.max_steps + 8
+    gathered = all_gather_rows(mine, nrows, dist, torch, device)
+    return merge_bothside(gathered[0], gathered[1]), mine

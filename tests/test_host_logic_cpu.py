@@ -571,3 +571,74 @@ def test_newton_hopf_known_answers():
                                zeta, zeta.copy(), opts, _dense_ls2, _dense_cls)
     assert s2.converged, s2.residuals
     assert abs(s2.p - gl.r_hopf()) < 1e-7 and abs(s2.omega - gl.nu) < 1e-7 and np.linalg.norm(s2.u) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------ bothside (the reference's own split)
+def _bothside_setup(bk):
+    P = bk.palc
+    F = lambda x, r: r + x - x**3
+    J = lambda x, r: np.diag(1 - 3 * x**2)
+    ls = krylov.DefaultLS()
+    cp = P.ContinuationPar(dsmin=0.001, dsmax=0.07, ds=0.02, p_max=1.5, p_min=-1.0, max_steps=150,
+                           newton_options=P.NewtonPar(tol=1e-10, linsolver=ls))
+    mk = lambda: NumpyProblem(F, J, np.array([0.8]), 0.2, record=lambda x: x[0])
+    return P, mk, P.PALC(bls=BlsAdapter(obls.MatrixBLS())), cp
+
+
+def test_bothside_merge_single_process():
+    """continuation(...; bothside = true) (src/Continuation.jl:687-700) + _merge (src/Results.jl:464-489) on r + x - x^3 started
+    in the middle of the branch: one monotone sweep of x from the p_min end to the p_max end, start point listed twice"""
+    bk = g.load_package()
+    P, mk, alg, cp = _bothside_setup(bk)
+    merged, _ = bk.segments.continuation_bothside(P, mk, alg, cp, P.norm2)
+    fwd, _ = P.continuation(mk(), alg, cp)
+    cpb = P.ContinuationPar(**{**cp.__dict__, "ds": -cp.ds})
+    bwd, _ = P.continuation(mk(), alg, cpb)
+    assert len(merged) == len(fwd) + len(bwd)
+    assert {merged[0, 0], merged[-1, 0]} == {-1.0, 1.5}                 # both parameter bounds are reached, one per direction
+    k = len(bwd)
+    assert merged[k - 1, 0] == merged[k, 0] == 0.2 and merged[k - 1, 1] == merged[k, 1]   # the common start point, twice
+    x = np.delete(merged[:, 1], k)
+    assert np.all(np.diff(x) > 0) or np.all(np.diff(x) < 0)             # one sweep along the curve, no gap and no overlap
+    assert np.max(np.abs(merged[:, 0] + merged[:, 1] - merged[:, 1] ** 3)) < 1e-9
+    # merge_bothside orders whatever ends coincide (src/Results.jl:470-487)
+    a = np.array([[0.0, 0.0, 0, 0], [1.0, 1.0, 0, 0]])
+    b = np.array([[0.0, 0.0, 0, 0], [-1.0, -1.0, 0, 0]])
+    M = bk.segments.merge_bothside
+    assert M(a, b)[:, 0].tolist() == [-1.0, 0.0, 0.0, 1.0] and M(a, b[::-1])[:, 0].tolist() == [-1.0, 0.0, 0.0, 1.0]
+    assert M(a[::-1], b)[:, 0].tolist() == [1.0, 0.0, 0.0, -1.0] and M(a, np.zeros((0, 4))).tolist() == a.tolist()
+
+
+def _bothside_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as gg
+    bk = gg.load_package()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, mk, alg, cp = _bothside_setup(bk)
+    merged, mine = bk.segments.continuation_bothside(P, mk, alg, cp, P.norm2, dist=dist, torch=torch, device="cpu")
+    q.put((rank, merged.tolist(), len(mine), mine[1]["param"] if len(mine) > 1 else None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bothside_two_ranks_gloo():
+    """one direction per rank, all_gather of the rows, the same merged branch on both ranks and the same as one process computes"""
+    import torch.multiprocessing as mp
+    bk = g.load_package()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_bothside_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    P, mk, alg, cp = _bothside_setup(bk)
+    single, _ = bk.segments.continuation_bothside(P, mk, alg, cp, P.norm2)
+    assert res[0][1] == res[1][1] and np.array_equal(np.array(res[0][1]), single)
+    assert res[0][3] > 0.2 and res[1][3] < 0.2 and res[0][2] + res[1][2] == len(single)   # rank 0 went up, rank 1 down
