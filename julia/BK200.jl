@@ -284,23 +284,23 @@ struct PalcResult           # == bk_palc_result
     work_newton::Int64; work_linear::Int64; p_final::Cdouble; ds_final::Cdouble
 end
 """
-    continuation_native(ctx, u0, params, lens::Int, alg::PALC, opts::ContinuationPar; normC = norm, u1 = nothing, p1 = 0.0)
+    continuation_native(ctx, u0, params, lens::Int, alg::PALC, contpar::ContinuationPar; normC = norm, u1 = nothing, p1 = 0.0)
 
 `lens` = 1-based index of the continuation parameter inside `params`.  `alg.bls` is a `BorderingBLSB200` or a `MatrixFreeBLSB200`,
-`opts.newton_options.linsolver` a `GMRESB200`.  Returns `(rows, result)`: `rows[:, k] = (param, ‖u‖, itnewton, itlinear, ds, step)`
+`contpar.newton_options.linsolver` a `GMRESB200`.  Returns `(rows, result)`: `rows[:, k] = (param, ‖u‖, itnewton, itlinear, ds, step)`
 like `br.branch` (src/Continuation.jl:259-272), `result::PalcResult`, and the last state in a `DeviceVec`.
 """
-function continuation_native(c::Context, u0, params, lens::Int, alg, opts; normC = norm, u1 = nothing, p1 = 0.0)
+function continuation_native(c::Context, u0, params, lens::Int, alg, contpar; normC = norm, u1 = nothing, p1 = 0.0)
     setparams!(c, params)
-    ls = opts.newton_options.linsolver
+    ls = contpar.newton_options.linsolver
     b = alg.bls
     bord = b isa BorderingBLSB200
-    po = Ref(PalcOpts(opts.ds, opts.dsmin, opts.dsmax, opts.a, opts.p_min, opts.p_max, alg.θ, opts.η, opts.newton_options.tol, 0.0,
-                      bord ? b.tol : 0.0, opts.max_steps, opts.newton_options.max_iterations, lens - 1,
+    po = Ref(PalcOpts(contpar.ds, contpar.dsmin, contpar.dsmax, contpar.a, contpar.p_min, contpar.p_max, alg.θ, contpar.η, contpar.newton_options.tol, 0.0,
+                      bord ? b.tol : 0.0, contpar.max_steps, contpar.newton_options.max_iterations, lens - 1,
                       alg.tangent isa BK.Bordered ? 1 : 0, bord ? 1 : 0, bord && b.check_precision ? 1 : 0, bord ? b.k : 1,
                       normC === BK.norminf ? 1 : 0))
     o = Ref(opts(ls))
-    maxrows = opts.max_steps + 8
+    maxrows = contpar.max_steps + 8
     rows = zeros(6, maxrows); res = Ref(PalcResult(0, 0, 0, 0, 0, 0, 0.0, 0.0)); uf = DeviceVec(c, c.N)
     st = GC.@preserve u0 u1 ccall((:bk_palc_run, lib), Int32,
         (Ptr{Cvoid}, Ptr{PalcOpts}, Ptr{GmresOpts}, Ptr{Float64}, Float64, Ptr{Float64}, Float64, Ptr{Float64}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{PalcResult}),
