@@ -189,7 +189,7 @@ Base.@kwdef struct BorderingBLSB200{S} <: BK.AbstractBorderedLinearSolver   # sr
     check_precision::Bool = true
     k::Int64 = 1
 end
-BorderingBLSB200(ls::GMRESB200) = BorderingBLSB200(solver = ls)
+BorderingBLSB200(ls::GMRESB200; k...) = BorderingBLSB200(; solver = ls, k...)   # BorderingBLS(solver; tol, check_precision, k), src/LinearBorderSolver.jl:59-75
 BK.update_bls(b::BorderingBLSB200, ls) = BorderingBLSB200(ls, b.tol, b.check_precision, b.k)   # src/LinearBorderSolver.jl:38,490-493
 
 struct MatrixFreeBLSB200{S} <: BK.AbstractBorderedLinearSolver                # src/LinearBorderSolver.jl:404-437
