@@ -341,3 +341,123 @@ def test_bordered_vec_reference_cases(vector_p):
     V.copyto(c, y)
     V.scale(c, 2.0)
     assert np.array_equal(cat(y), [4, 5, 6])
+
+
+# ------------------------------------------------------------------------------------------------ test/hopf_codim_2/testHopfMA.jl
+def Fbru(x, q):
+    """1-D Brusselator, test/hopf_codim_2/testHopfMA.jl:7-29 (q = (alpha, beta, D1, D2, l), Dirichlet values alpha, beta / alpha)"""
+    al, be, D1, D2, l = q
+    n = len(x) // 2
+    h2 = (1.0 / n) ** 2
+    c1, c2 = D1 / l**2 / h2, D2 / l**2 / h2
+    u, v = x[:n], x[n:]
+    up = np.concatenate([[al], u, [al]])
+    vp = np.concatenate([[be / al], v, [be / al]])
+    f = np.empty_like(x)
+    f[:n] = c1 * (up[:-2] - 2 * u + up[2:]) + al - (be + 1) * u + u**2 * v
+    f[n:] = c2 * (vp[:-2] - 2 * v + vp[2:]) + be * u - u**2 * v
+    return f
+
+
+def Jbru(x, q):
+    """:33-64 (Jbru_sp, dense here)"""
+    al, be, D1, D2, l = q
+    n = len(x) // 2
+    h2 = (1.0 / n) ** 2
+    c1, c2 = D1 / l**2 / h2, D2 / l**2 / h2
+    u, v = x[:n], x[n:]
+    T = lambda c: c * (np.diag(np.ones(n - 1), 1) + np.diag(np.ones(n - 1), -1) - 2 * np.eye(n))
+    return np.block([[T(c1) + np.diag(-(be + 1) + 2 * u * v), np.diag(u * u)],
+                     [np.diag(be - 2 * u * v), T(c2) + np.diag(-u * u)]])
+
+
+def test_hopf_ma_linear_solver_on_the_brusselator_pde():
+    """testHopfMA.jl:67-141 on its own problem (n = 10, continuation in l from the uniform state): the first Hopf point of the
+    branch refined by newton_hopf, then the structural check of the reference test -- the linear solver of the minimally
+    augmented system (HopfLinearSolverMinAug, sigma_x / sigma_p / sigma_omega by finite differences) against the
+    finite-difference Jacobian of the functional (x, p, omega) -> (F, Re sigma, Im sigma) -- and 3 steps of the Hopf curve in beta
+    (:159-162)."""
+    bk = g.load_package()
+    P, C2 = bk.palc, bk.codim2
+    n = 10
+    par = [2.0, 5.45, 0.008, 0.004, 0.3]
+    x0 = np.concatenate([np.full(n, par[0]), np.full(n, par[1] / par[0])])      # the uniform state solves F = 0 for every l
+    assert np.linalg.norm(Fbru(x0, par)) < 1e-12
+    E = np.eye(2 * n)
+    Jfd = np.column_stack([(Fbru(x0 + 1e-6 * E[:, j], par) - Fbru(x0 - 1e-6 * E[:, j], par)) / 2e-6 for j in range(2 * n)])
+    assert np.max(np.abs(Jfd - Jbru(x0, par))) < 1e-6                            # :72-73 (Jbru_sp == Jbru_ana)
+    prob = NumpyProblem2(Fbru, Jbru, x0, par, 4)
+    cprob = DenseComplexProblem2(prob)
+    # first Hopf point along l (the branch of :76-77): leading complex pair crosses the axis
+    ls_ = np.linspace(0.3, 1.8, 301)
+    lead = [max((ev.real for ev in np.linalg.eigvals(Jbru(x0, prob._par(l))) if abs(ev.imag) > 1e-8), default=np.nan) for l in ls_]
+    i = next(k for k in range(len(ls_) - 1) if lead[k] < 0 <= lead[k + 1])
+    l0 = ls_[i + 1]
+    vals, vecs = np.linalg.eig(Jbru(x0, prob._par(l0)))
+    kk = int(np.argmax(np.where(np.abs(vals.imag) > 1e-8, vals.real, -np.inf) + 1e-9 * np.sign(vals.imag)))
+    valt, vect = np.linalg.eig(Jbru(x0, prob._par(l0)).T)
+    kt = int(np.argmin(np.abs(valt - np.conj(vals[kk]))))
+    opts = P.NewtonPar(tol=1e-11, max_iterations=15, linsolver=krylov.DefaultLS())
+    hp = C2.newton_hopf(prob, cprob, x0, l0, vals[kk].imag, vecs[:, kk], vect[:, kt], opts, _dense_ls2, _dense_cls)
+    assert hp.converged and hp.itnewton <= 6, hp.residuals                        # :80-81, 139-140
+    ev = np.linalg.eigvals(Jbru(hp.u, prob._par(hp.p)))
+    j = int(np.argmin(np.abs(ev - 1j * abs(hp.omega))))
+    assert abs(ev[j].real) < 1e-9 and abs(ev[j].imag - abs(hp.omega)) < 1e-9
+    # the MA functional and its linear solver at the Hopf point (:92-137)
+    ma = C2.HopfMinAug(prob, cprob, vect[:, kt], vecs[:, kk], _dense_ls2, _dense_cls)
+
+    def H(z):
+        F, sr, si = ma.residual(z[:-2].copy(), z[-2], z[-1])
+        return np.concatenate([F, [sr, si]])
+    z0 = np.concatenate([hp.u, [hp.p, hp.omega]])
+    m = len(z0)
+    I = np.eye(m)
+    eps = 1e-6
+    Jma = np.column_stack([(H(z0 + eps * I[:, c]) - H(z0 - eps * I[:, c])) / (2 * eps) for c in range(m)])
+    rhs = np.random.default_rng(5).random(m)
+    sol_fd = np.linalg.solve(Jma, rhs)
+    dX, dp, dom, _ = ma.solve(hp.u.copy(), hp.p, hp.omega, rhs[:-2].copy(), rhs[-2], rhs[-1])
+    sol_ma = np.concatenate([dX, [dp, dom]])
+    assert np.linalg.norm(sol_ma - sol_fd) < 1e-3 * np.linalg.norm(sol_fd), (sol_ma[-2:], sol_fd[-2:])
+    # sigma_p, sigma_omega, sigma_x of the solver against the finite-difference Jacobian (:124-137: rtol 1e-4, 1e-4, 1e-3)
+    v, w, dpF, sigma_p, sigma_om = ma.bordered_terms(hp.u, hp.p, hp.omega)
+    assert abs(sigma_p - complex(Jma[-2, -2], Jma[-1, -2])) < 1e-4 * abs(sigma_p)
+    assert abs(sigma_om - complex(Jma[-2, -1], Jma[-1, -1])) < 1e-4 * abs(sigma_om)
+    assert np.max(np.abs(Jma[:-2, -2] - dpF)) < 1e-5 * max(1.0, np.max(np.abs(dpF))) and np.max(np.abs(Jma[:-2, -1])) < 1e-7
+    # three steps of the Hopf curve in beta (:159-162)
+    cp = P.ContinuationPar(dsmin=0.001, dsmax=0.05, ds=0.01, p_min=0.0, p_max=6.5, max_steps=3, newton_options=opts)
+    prob.params[4] = hp.p
+    prob.lens = 4
+    curve = C2.continuation_hopf(prob, cprob, hp.u, hp.p, hp.omega, 1, vecs[:, kk], vect[:, kt], cp, _dense_ls2, _dense_cls)
+    assert len(curve.rows) == 4 and curve.p2[0] == 5.45 and curve.p2[-1] > 5.45
+    for l_k, be_k, om_k in zip(curve.p1, curve.p2, curve.omega):
+        q = list(par)
+        q[4], q[1] = l_k, be_k
+        xk = np.concatenate([np.full(n, q[0]), np.full(n, q[1] / q[0])])
+        ev = np.linalg.eigvals(Jbru(xk, q))
+        assert np.min(np.abs(ev - 1j * abs(om_k))) < 1e-8
+
+
+def test_fold_ma_linear_solver_against_finite_differences(com_fold):
+    """test/fold_codim_2/testJacobianFoldDeflation.jl pattern on the CO model: the linear solver of the minimally augmented Fold
+    system (foldMALinearSolver, sigma_x / sigma_p by finite differences, MinAugFold.jl:122-146) against the finite-difference
+    Jacobian of (x, p) -> (F, sigma) at the Fold point -- for a non-symmetric Jacobian (J' through jacobian_adjoint)"""
+    bk, prob, ls, bls, sol, t = com_fold
+    C2 = bk.codim2
+    rng = np.random.default_rng(7)
+    a, b = t + 0.1 * rng.standard_normal(3), t + 0.1 * rng.standard_normal(3)     # generic border vectors
+    ma = C2.FoldMinAug(prob, a, b, bls, symmetric=False)
+
+    def H(z):
+        F, sigma = ma.residual(z[:-1].copy(), z[-1])
+        return np.concatenate([F, [sigma]])
+    z0 = np.concatenate([sol.u, [sol.p]]) + 1e-3 * rng.standard_normal(4)          # near, not on, the Fold: sigma != 0
+    I = np.eye(4)
+    eps = 1e-6
+    Jma = np.column_stack([(H(z0 + eps * I[:, c]) - H(z0 - eps * I[:, c])) / (2 * eps) for c in range(4)])
+    rhs = rng.random(4)
+    dX, dp, cv = ma.solve(z0[:-1].copy(), z0[-1], rhs[:-1].copy(), rhs[-1])
+    ref = np.linalg.solve(Jma, rhs)
+    assert cv and np.linalg.norm(np.concatenate([dX, [dp]]) - ref) < 1e-4 * np.linalg.norm(ref)
+    v, w, dpF, sigma_p = ma.bordered_terms(z0[:-1].copy(), z0[-1])
+    assert abs(sigma_p - Jma[-1, -1]) < 1e-5 * max(1.0, abs(sigma_p)) and np.max(np.abs(dpF - Jma[:-1, -1])) < 1e-6
