@@ -434,9 +434,19 @@ def main():
         assert ok, "CPU Newton to the front failed"
         t_setup = time.perf_counter() - t_setup
         nb = max(1, min(K, args.ref_batches))
+        cb.reset_counters()
         rows, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], fr, PAR[0], cpp_opts(cb, nb * B, thr))
         nst = len(rows) - 1
         v = nst / secs
+        try:  # how close the CPU arm itself runs to its host's memory system (informational)
+            b1, sp = cb.counters()
+            triad = cb.triad_gbs(thr)
+            host_roofline = {"bound": "host dram", "achieved": (b1 + sp) / secs * 1e-9, "peak": triad, "unit": "GB/s", "frac": (b1 + sp) / secs * 1e-9 / triad,
+                             "note": "algorithmic bytes of the MGS / BLAS-1 sweeps (dot 16 N, axpy 24 N) and the CSR SpMVs (12 B per entry + vectors) of the sample, "
+                                     "the preconditioner's FFT passes not counted, over the loop time; peak = STREAM triad on the same threads",
+                             "blas1_gbytes": b1 * 1e-9, "spmv_gbytes": sp * 1e-9}
+        except Exception as exc:
+            host_roofline = {"error": repr(exc)}
         print(json.dumps({"metric": metric, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
                           "ms_per_step": 1e3 * B / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "impl": "reference",
@@ -445,7 +455,8 @@ def main():
                           "cpu_baseline": {"value": v, "unit": "steps/s", "cores": thr, "kind": "port",
                                            "sample": f"the first {nst} continuation steps ({nb} of {K} batches) of the window from the converged front; "
                                                      f"C++17/OpenMP restatement (oracle/c: CSR SpMV with the kron-assembled L1, MGS GMRES, pair-FFT DCT Pr) on {thr} threads "
-                                                     f"(fastest of the calibrated counts; the host offers {cb.load().bkcpu_max_threads()})"},
+                                                     f"(fastest of the calibrated counts; the host offers {cb.load().bkcpu_max_threads()})",
+                                           "host_roofline": host_roofline},
                           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 

@@ -92,17 +92,22 @@ struct PVec {
 typedef PVec<double> vec;
 
 // ------------------------------------------------------------------------------------------------ BLAS-1 (OpenMP)
+// algorithmic bytes moved by the BLAS-1 sweeps and the SpMVs since the last bkcpu_reset_counters (control thread only)
+static double g_blas1_bytes = 0, g_spmv_bytes = 0;
 inline double dot(const double* a, const double* b, long n) {
+  g_blas1_bytes += 16.0 * (double)n;
   double s = 0;
 #pragma omp parallel for reduction(+ : s) schedule(static)
   for (long i = 0; i < n; ++i) s += a[i] * b[i];
   return s;
 }
 inline void axpy(double* y, double a, const double* x, long n) {  // y += a x
+  g_blas1_bytes += 24.0 * (double)n;
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n; ++i) y[i] += a * x[i];
 }
 inline void scal_copy(double* y, double a, const double* x, long n) {  // y = a x
+  g_blas1_bytes += 16.0 * (double)n;
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n; ++i) y[i] = a * x[i];
 }
@@ -120,6 +125,7 @@ struct Csr {
   PVec<int> col;
   vec val;
   void spmv(const double* x, double* y) const {
+    g_spmv_bytes += 12.0 * (double)ptr[n] + 8.0 * (double)(n + 1) + 16.0 * (double)n;  // val + col, row pointers, x (once) and y
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < n; ++i) {
       double s = 0;
@@ -655,6 +661,35 @@ int32_t bkcpu_sh2d_palc(int32_t nx, int32_t ny, double lx, double ly, double nu,
   if (work_newton) *work_newton = wn;
   if (work_linear) *work_linear = wl;
   return 0;
+}
+
+// measurement aids for bench.py's CPU arm: algorithmic bytes of the BLAS-1 sweeps (dot 16 N, axpy 24 N, scaled copy 16 N) and of
+// the CSR SpMVs (12 B per stored entry + row pointers + both vectors) since the last reset, and the host's own streaming
+// bandwidth (STREAM triad a = b + s c over three 256 MB arrays first-touched by the same team) to set them against
+void bkcpu_reset_counters() { g_blas1_bytes = g_spmv_bytes = 0; }
+void bkcpu_counters(double out[2]) {
+  out[0] = g_blas1_bytes;
+  out[1] = g_spmv_bytes;
+}
+double bkcpu_triad_gbs(int32_t nthreads) {
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+  const long n = 32L * 1024 * 1024;
+  vec a((size_t)n), b((size_t)n), c((size_t)n);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) {
+    a[i] = 0.0;
+    b[i] = 1.0;
+    c[i] = 2.0;
+  }
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    const auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) a[i] = b[i] + 3.0 * c[i];
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rep > 0) best = std::max(best, 24.0 * (double)n / dt * 1e-9);
+  }
+  return best + 0.0 * a[n / 2];
 }
 
 // processors available to this process (affinity-aware); NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1

@@ -81,3 +81,21 @@ def palc(dims, lengths, nu, u_start, p_start, opts):
     out = [dict(param=float(r[0]), x=float(r[1]), itnewton=int(r[2]), itlinear=int(r[3]), ds=float(r[4]), step=i)
            for i, r in enumerate(rows[: nrows.value])]
     return out, secs.value, tstep[: nrows.value].copy(), ufin, (wn.value, wl.value)
+
+
+def reset_counters():
+    load().bkcpu_reset_counters()
+
+
+def counters():
+    """algorithmic bytes since reset_counters(): (BLAS-1 sweeps, CSR SpMVs)"""
+    out = (C.c_double * 2)()
+    load().bkcpu_counters(out)
+    return float(out[0]), float(out[1])
+
+
+def triad_gbs(nthreads=0):
+    """the host's streaming bandwidth with `nthreads` OpenMP threads (STREAM triad), GB/s"""
+    lib = load()
+    lib.bkcpu_triad_gbs.restype = C.c_double
+    return float(lib.bkcpu_triad_gbs(C.c_int32(nthreads)))
