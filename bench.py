@@ -434,7 +434,10 @@ def main():
         assert ok, "CPU Newton to the front failed"
         t_setup = time.perf_counter() - t_setup
         nb = max(1, min(K, args.ref_batches))
-        cb.reset_counters()
+        try:
+            cb.reset_counters()
+        except Exception:
+            pass
         rows, secs, tstep, _, work = cb.palc((n, n), domain(n), PAR[1], fr, PAR[0], cpp_opts(cb, nb * B, thr))
         nst = len(rows) - 1
         v = nst / secs
