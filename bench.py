@@ -21,6 +21,10 @@ The alternative `--partition scout` cuts ONE branch window into chunks seeded by
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 1024] [--batch 10] [--impl reference]
 
+Besides `e2e` (the plugin surfaces with host vectors) the line carries `e2e_native`: the same window through ONE C-ABI call from and
+to host buffers (bk_palc_run, the PALC loop as host C++ inside the library), with a check that its rows equal the device-resident
+run's bit for bit.
+
 --impl reference : times the CPU restatement of the reference path -- oracle/c, C++17/OpenMP on all host cores (CSR SpMV with the
 kron-assembled L1, MGS GMRES, DCT preconditioner); Julia is absent from this image, see DESIGN.md -- on a
 bounded sample of the same window.
@@ -545,6 +549,42 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- the same job through ONE C-ABI call from and to host buffers: bk_palc_run (include/bk200.h; the PALC loop as host C++
+    # inside the library, same kernels in the same order as the plugin path above).  Rank 0's own run; replicas are identical.
+    e2e_native = None
+    if not args.no_e2e and (replicas or world == 1):
+        try:
+            Pn = bk.palc
+            alg_n, cpf_n, _, _ = make_algs(bk, ctx, ls, n)
+            cpn = cpf_n()
+            cpn.max_steps = K * B
+            u_host = ctx.pinned_array(u_front.numpy())
+            prob_n = Pn.BifurcationProblemB200(ctx, u_host, list(PAR), lens=0)
+            ctx.sync()
+            ctx.set_timing(0)
+            sn0 = ctx.stats()
+            st_n = torch.cuda.ExternalStream(ctx.lib.bk_stream(ctx.handle))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(st_n)
+            rows_n, info_n = Pn.continuation_native(prob_n, alg_n, cpn, normC=Pn.norminf)
+            info_n["u"].numpy()  # the final state back on the host, inside the timed region
+            ev1.record(st_n)
+            ctx.sync()
+            ms_n = float(ev0.elapsed_time(ev1))
+            sn1 = ctx.stats()
+            rows_n = rows_n[: K * B + 1]
+            same = len(rows_n) == len(rows) and all(a["param"] == b["param"] and a["x"] == b["x"] and a["itlinear"] == b["itlinear"]
+                                                    for a, b in zip(rows_n, rows))
+            e2e_native = {"value": (world if replicas else 1) * K * B / (ms_n * 1e-3), "unit": "steps/s",
+                          "h2d_bytes_per_step": int((sn1["h2d_bytes"] - sn0["h2d_bytes"]) / K), "d2h_bytes_per_step": int((sn1["d2h_bytes"] - sn0["d2h_bytes"] + 8 * 6 * len(rows_n)) / K),  # final state (counted by the library) + the rows
+                          "abi_calls": 1, "rows_identical_to_the_device_resident_run": bool(same),
+                          "corrector_work": {"newton_its": int(info_n["work_newton"]), "linear_its": int(info_n["work_linear"]), "rejected_steps": int(info_n["nfail"])},
+                          "note": "bk_palc_run(ctx, opts, linsolver, u0 [host], ..., rows [host], u_final): one C-ABI call for the whole window; start vector uploaded "
+                                  "once, rows and the final state returned to the host; CUDA events around the call on the library's stream"
+                                  + ("; rank 0's run x the number of (identical, independent) replicas" if replicas else "")}
+        except Exception as exc:  # an extra measurement: it must never cost the line
+            e2e_native = {"error": repr(exc)}
+
     value = (world if replicas else 1) * K * B / (tmax * 1e-3)
     nst = len(branch)
     peak, peak_src = measured_peak()
@@ -575,7 +615,7 @@ def main():
                                 f"(ds x{SCOUT['ds_factor']:g}, Newton tol {SCOUT['newton_tol']:g}, GMRES reltol {SCOUT['gmres_reltol']:g})")),
                "per_rank": per_rank, "scout_ms": info["scout_ms"], "scout_points": info["scout_points"],
                "lambda_range": [float(branch[:, 0].min()), float(branch[:, 0].max())] if nst else None}),
-           "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline, "e2e": e2e}
+           "clocks": clocks, "gpu_launches": int(delta.get("kernel_launches", 0)), "roofline": roofline, "e2e": e2e, "e2e_native": e2e_native}
 
     # ---- the GPU arm on the reference arm's sample: `--impl reference` times the first ref_batches batches of the window (a bounded
     # sample, cheaper per step than the window's average: the Krylov counts grow along the branch), `value` the whole window
