@@ -56,4 +56,4 @@ def test_transform_kernels_stage_their_tables_by_bulk_copy(sass):
     tr = {k: c for k, c in cnt.items() if re.search(r"k_strided|k_contig", k)}
     assert len(tr) >= 30
     for k, c in tr.items():
-        assert c["UBLKCP"] >= 2 and c["SYNCS"] >= 1 and c["DFMA"] >= 50, (k, dict(c))
+        assert c["UBLKCP"] >= 2 and c["SYNCS"] >= 1 and c["DFMA"] >= 10, (k, dict(c))
