@@ -57,3 +57,25 @@ def test_transform_kernels_stage_their_tables_by_bulk_copy(sass):
     assert len(tr) >= 30
     for k, c in tr.items():
         assert c["UBLKCP"] >= 2 and c["SYNCS"] >= 1 and c["DFMA"] >= 10, (k, dict(c))
+
+
+def test_ring_kernels_fit_four_ctas_per_sm():
+    """bk_krylov.cu plans BK2_BLOCKS_PER_SM = 4 CTAs of 288 threads per SM (grid sizing, shared-memory budget): that needs
+    <= 65536 / (4 x 288) = 56 registers per thread and no stack frame; read from the built library (cuobjdump --dump-resource-usage)"""
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    bk = g.load_package()
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", bk.lib.LIB_PATH], capture_output=True, text=True).stdout
+    seen = 0
+    fn = None
+    for l in out.splitlines():
+        m = re.search(r"Function (\S+):", l)
+        if m:
+            fn = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+)\s+STACK:(\d+)", l)
+        if m and fn and re.search(r"k2_(fused|update|dots)", fn):
+            assert int(m.group(1)) <= 56 and int(m.group(2)) == 0, (fn, l.strip())
+            seen += 1
+            fn = None
+    assert seen >= 32    # k2_fused<1..8, false / true>, k2_update<1..8>, k2_dots<1..8>
