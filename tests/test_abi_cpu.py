@@ -74,3 +74,27 @@ def test_hessenberg_eig_golden_5x5():
     T = T + np.triu(T, 1).T
     vals, _ = bk.hessenberg_eig(T, vectors=False)
     assert np.allclose(np.sort(vals.real), np.linalg.eigvalsh(T), atol=1e-10) and np.abs(vals.imag).max() < 1e-10
+
+
+def test_header_is_plain_c_and_a_c_caller_links_and_fails_loudly(tmp_path):
+    """include/bk200.h is valid C99 (the Julia ccall / cgo / JNI side sees a C ABI), and a plain C program -- tools/palc_cli, the
+    native driver over bk_palc_run -- builds against libbk200.so with no C++ or torch in sight; without a GPU it must stop with the
+    library's own error message, not fall back to anything."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    bk = g.load_package()
+    if not os.path.exists(bk.lib.LIB_PATH):
+        bk.build()
+    exe = str(tmp_path / "bk_palc_cli")
+    libdir = os.path.dirname(bk.lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tools", "palc_cli", "bk_palc_cli.c"), "-o", exe, "-L", libdir, "-lbk200", "-lm",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run itself is a GPU job")
+    run = subprocess.run([exe, "--grid", "64", "--steps", "2"], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 2 and "bk_ctx_create failed" in run.stderr and run.stdout == ""
