@@ -552,7 +552,7 @@ def main():
     # ---- the same job through ONE C-ABI call from and to host buffers: bk_palc_run (include/bk200.h; the PALC loop as host C++
     # inside the library, same kernels in the same order as the plugin path above).  Rank 0's own run; replicas are identical.
     e2e_native = None
-    if not args.no_e2e and (replicas or world == 1):
+    if not args.no_e2e and world == 1:  # N = 1 only: at N > 1 the other ranks have left by now and rank 0 should not linger
         try:
             Pn = bk.palc
             alg_n, cpf_n, _, _ = make_algs(bk, ctx, ls, n)
