@@ -580,7 +580,8 @@ def main():
                           "abi_calls": 1, "rows_identical_to_the_device_resident_run": bool(same),
                           "corrector_work": {"newton_its": int(info_n["work_newton"]), "linear_its": int(info_n["work_linear"]), "rejected_steps": int(info_n["nfail"])},
                           "note": "bk_palc_run(ctx, opts, linsolver, u0 [host], ..., rows [host], u_final): one C-ABI call for the whole window; start vector uploaded "
-                                  "once, rows and the final state returned to the host; CUDA events around the call on the library's stream"
+                                  "once, rows and the final state returned to the host; CUDA events around the call on the library's stream; no L2 flush inside the call "
+                                  "(the Krylov basis of a solve exceeds L2)"
                                   + ("; rank 0's run x the number of (identical, independent) replicas" if replicas else "")}
         except Exception as exc:  # an extra measurement: it must never cost the line
             e2e_native = {"error": repr(exc)}
