@@ -161,9 +161,12 @@ class BorderedVec:
         self.p = src.p if np.ndim(src.p) == 0 else src.p.copy()
         return self
 
-    def zero_(self):
-        V.scale(self.u, 0.0)
-        self.p = self.p * 0.0
+    def zero_(self):                   # VI.zerovector!: exact zeros (0 * NaN would stay NaN)
+        if hasattr(self.u, "zero_"):
+            self.u.zero_()
+        else:
+            self.u[...] = 0.0
+        self.p = 0.0 if np.ndim(self.p) == 0 else np.zeros_like(self.p)
         return self
 
     def scale_(self, a):

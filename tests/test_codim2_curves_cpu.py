@@ -461,3 +461,11 @@ def test_fold_ma_linear_solver_against_finite_differences(com_fold):
     assert cv and np.linalg.norm(np.concatenate([dX, [dp]]) - ref) < 1e-4 * np.linalg.norm(ref)
     v, w, dpF, sigma_p = ma.bordered_terms(z0[:-1].copy(), z0[-1])
     assert abs(sigma_p - Jma[-1, -1]) < 1e-5 * max(1.0, abs(sigma_p)) and np.max(np.abs(dpF - Jma[:-1, -1])) < 1e-6
+
+
+def test_bordered_vec_zero_is_exact_even_from_nan():
+    bk = g.load_package()
+    BV, V = bk.codim2.BorderedVec, bk.palc.V
+    for p in (np.nan, np.array([np.nan, 1.0])):
+        z = V.zeros_like(BV(np.array([np.nan, 2.0]), p))
+        assert np.all(z.u == 0.0) and np.all(np.atleast_1d(z.p) == 0.0)
