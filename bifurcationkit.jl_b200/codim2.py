@@ -106,16 +106,18 @@ class FoldMinAug:
         self.itlinear += int(np.sum(it))
         return dX, dp, cv
 
-    def update(self, x, p):
+    def update(self, x, p, keep_borders=False):
         """update!(probma, iter, state) (MinAugFold.jl:276-309) and test_bt_cusp (:551-575): after an accepted step the border
-        vectors follow the null vectors, a <- w / ||w||, b <- v / ||v||; BT = <w / ||w||, v / ||v||>"""
+        vectors follow the null vectors, a <- w / ||w||, b <- v / ||v||; BT = <w / ||w||, v / ||v||>.  keep_borders: only the
+        test function (inside an event bisection the reference leaves a, b alone, :287-289)."""
         J = self.prob.J(x, p)
         v, _ = self._border(J, self.a, self.b)
         w, _ = self._border(J if self.symmetric else self._Jt(x, p), self.b, self.a)
         V.scale(v, 1.0 / self.norm(v))
         V.scale(w, 1.0 / self.norm(w))
-        V.copyto(self.a, w)
-        V.copyto(self.b, v)
+        if not keep_borders:
+            V.copyto(self.a, w)
+            V.copyto(self.b, v)
         self.BT = V.dot(w, v)
         return self.BT
 
@@ -256,6 +258,73 @@ class BorderingBLSHost:
 
 
 @dataclass
+class Codim2Point:
+    """an entry of br.specialpoint on a codim-2 curve: type "bt" | "cusp", param = p2, p1, and the state of the located point"""
+    type: str
+    param: float
+    p1: float
+    step: int
+    status: str      # converged | guess | guessL (locate_event!)
+    interval: tuple
+    x: object
+
+
+def locate_event(it, _st, values_at, labels):
+    """locate_event!(event, iter, state) (src/events/EventDetection.jl:28-235) for a ContinuousEvent whose indicator is the number of
+    positive test functions (nb_signs): bisection on ds from the state `_st` just AFTER the event -- first half a step back, then
+    halving, reversing at every change of the indicator -- until contpar.n_inversion reversals (or max_bisection_steps /
+    dsmin_bisection).  On return `_st` holds the located state (just after the event for an even number of reversals) and its
+    predictor.  values_at(st) -> tuple of test-function values at a state.  Returns (status, interval, label)."""
+    from . import events as E
+    from .palc import _predict
+    cp = it.contpar
+    nb = lambda vals: sum(1 for v in vals if v > 0)
+    if abs(_st.ds) < cp.dsmin:
+        return "none", (0.0, 0.0), None
+    v_after = values_at(_st)
+    after, st, before = E.copy_state(_st), E.copy_state(_st), E.copy_state(_st)
+    st.in_bisection = True
+    before.zold_p, before.z_p = before.z_p, before.zold_p
+    st.ds *= -1
+    st.step = 0
+    st.stepsizecontrol = False
+    nsigns = [nb(v_after)]
+    interval = list(E.getinterval(st.z_p, st.zold_p))
+    indinterval = 0 if interval[0] == st.z_p else 1
+    n_inversion, alive, vals = 0, True, v_after
+    changed = None
+    while True:
+        if not st.converged or not alive:
+            break
+        prev, vals = vals, values_at(st)      # update_event!: on the first pass this is the state the bisection starts from
+        nsigns.append(nb(vals))
+        if nsigns[-1] == nsigns[-2]:
+            st.ds /= 2                        # the event is still ahead of the current state
+        else:
+            st.ds /= -2                       # passed it: reverse
+            n_inversion += 1
+            indinterval = 1 - indinterval
+            changed = [k for k, (a_, b_) in enumerate(zip(prev, vals)) if (a_ > 0) != (b_ > 0)]
+        _predict(st)
+        E.copyto_state(after if n_inversion % 2 == 0 else before, st)
+        if st.step > 0:
+            interval[indinterval] = st.z_p
+        if not (abs(st.ds) >= cp.dsmin_bisection and st.step < cp.max_bisection_steps and n_inversion < cp.n_inversion):
+            break
+        alive = it.iterate(st)
+    if n_inversion % 2 == 0:
+        status, src, interval = ("converged" if n_inversion >= cp.n_inversion else "guess"), st, (st.z_p, before.z_p)
+    else:
+        status, src, interval = "guessL", after, (st.z_p, after.z_p)
+    for k in ("z_u", "zold_u", "tau_u", "zpred_u"):
+        V.copyto(getattr(_st, k), getattr(src, k))
+    _st.z_p, _st.zold_p, _st.tau_p, _st.zpred_p = src.z_p, src.zold_p, src.tau_p, src.zpred_p
+    _st.work_newton, _st.work_linear = st.work_newton, st.work_linear
+    _predict(_st)                             # update_predictor!(_state, iter) with the outer ds
+    return status, E.getinterval(*interval), (labels[changed[0]] if changed else None)
+
+
+@dataclass
 class FoldCurve:
     rows: list      # palc rows: param = p2, x = record (default p1), itnewton, itlinear, ds, step
     p1: list        # the Fold curve (p1[k], p2[k])
@@ -264,16 +333,20 @@ class FoldCurve:
     CP: list        # p1-component of the tangent: zero at a cusp
     ma: object
     state: object
+    specialpoint: list = None   # Codim2Point entries (detect_event > 0)
 
 
 def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls, alg=None, normC=V.norminf, symmetric=True,
-                      update_minaug_every_step=1, record=None, callback=None):
+                      update_minaug_every_step=1, record=None, callback=None, detect_event=0):
     """Codim-2 continuation of a Fold point in the parameters (p1 = params[prob.lens], p2 = params[lens2]):
     continuation_fold(prob, alg, foldpointguess, par, lens1, lens2, eigenvec, eigenvec_ad, options_cont; jacobian_ma = MinAug())
     (MinAugFold.jl:366-452).  PALC on the minimally augmented system, Newton linear solver = FoldLinearSolverMinAug over the
     bordered solver `bls` (bdlinsolver: MatrixFreeBLSB200 / BorderingBLSB200 on the device), outer bordered solver =
     BorderingBLS(that solver, check_precision = false), border vectors updated after every accepted step (update!), the
-    Bogdanov-Takens and cusp test functions recorded along the curve."""
+    Bogdanov-Takens and cusp test functions recorded along the curve.  detect_event = 1: a change of sign of a test function
+    between two points is recorded as a special point ("bt" / "cusp", the event of :428-431); = 2: it is located by the reference's
+    bisection (locate_event) with contpar.n_inversion / max_bisection_steps / dsmin_bisection, and the curve goes on from the
+    located state, as in the reference."""
     from . import palc as P
     ma = FoldMinAug(prob, eigenvec_ad, eigenvec, bls, symmetric=symmetric, norm=normC)
     z0 = BorderedVec(V.copy(x0), p1_0)
@@ -284,16 +357,37 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
                               "detect_bifurcation": 0})
     alg = alg or P.PALC()
     alg = P.PALC(tangent=alg.tangent, theta=alg.theta, bls=BorderingBLSHost(fls))
-    curve = FoldCurve([], [], [], [], [], ma, None)
+    curve = FoldCurve([], [], [], [], [], ma, None, [])
+    from . import events as E
+    it = E._Iter(pb, alg, cp, normC)
+
+    def values_at(s):   # test_bt_cusp at a state, the border vectors untouched
+        pb._set2(s.z_p)
+        return (ma.update(s.z_u.u, s.z_u.p, keep_borders=True), s.tau_u.p)
 
     def cb(st):
         pb._set2(st.z_p)
         if st.step % update_minaug_every_step == 0:
             ma.update(st.z_u.u, st.z_u.p)
+        else:
+            ma.update(st.z_u.u, st.z_u.p, keep_borders=True)
+        vals = (ma.BT, st.tau_u.p)
+        if detect_event > 0 and curve.BT and st.step > 0:
+            prev = (curve.BT[-1], curve.CP[-1])
+            flips = [k for k in range(2) if (prev[k] > 0) != (vals[k] > 0)]
+            if flips:
+                status, interval, label = "guess", E.getinterval(curve.p2[-1], st.z_p), ("bt", "cusp")[flips[0]]
+                if detect_event > 1:
+                    status, interval, lab = locate_event(it, st, values_at, ("bt", "cusp"))
+                    label = lab or label
+                    pb._set2(st.z_p)
+                    vals = (ma.update(st.z_u.u, st.z_u.p, keep_borders=True), st.tau_u.p)
+                if status != "none":
+                    curve.specialpoint.append(Codim2Point(label, st.z_p, st.z_u.p, st.step, status, tuple(interval), V.copy(st.z_u.u)))
         curve.p1.append(st.z_u.p)
         curve.p2.append(st.z_p)
-        curve.BT.append(ma.BT)
-        curve.CP.append(st.tau_u.p)
+        curve.BT.append(vals[0])
+        curve.CP.append(vals[1])
         return True if callback is None else callback(st)
 
     p2_0 = prob.params[lens2]

@@ -469,3 +469,31 @@ def test_bordered_vec_zero_is_exact_even_from_nan():
     for p in (np.nan, np.array([np.nan, 1.0])):
         z = V.zeros_like(BV(np.array([np.nan, 2.0]), p))
         assert np.all(z.u == 0.0) and np.all(np.atleast_1d(z.p) == 0.0)
+
+
+def test_bogdanov_takens_point_located_as_in_the_reference(com_fold):
+    """test/fold_codim_2/codim2.jl:75-90 with its own options -- continuation(br, 3, (@optic _.k), ContinuationPar(opts_br, p_max = 1.,
+    p_min = 0., max_steps = 50, detect_event = 2), update_minaug_every_step = 1, jacobian_ma = MinAug()); opts_br: ds = 0.002, dsmax = 0.01,
+    n_inversion = 4, max_bisection_steps = 25, Newton tol 1e-12 (the NewtonPar default) with max_iterations = 10, normC = norm:
+        sn_br.specialpoint[1].type == :bt,   sn_br.specialpoint[1].param ≈ 0.9716038596420551  (rtol 1e-5 there).
+    The located parameter is the end point of the event bisection, so it pins the whole chain -- the branch in q2, the Fold
+    refinement, 47 adaptive PALC steps on the minimally augmented system and the bisection -- not just the Bogdanov-Takens point."""
+    bk, prob, ls, bls, sol, t = com_fold
+    P, C2 = bk.palc, bk.codim2
+    t2 = t / np.linalg.norm(t)
+    s12 = C2.newton_fold(prob, sol.u, sol.p, t2, t2, P.NewtonPar(tol=1e-12, max_iterations=10, linsolver=ls), bls, symmetric=False)
+    assert s12.converged
+    cpf = P.ContinuationPar(p_min=0.0, p_max=1.0, ds=0.002, dsmax=0.01, dsmin=1e-4, max_steps=50, n_inversion=4, max_bisection_steps=25,
+                            newton_options=P.NewtonPar(tol=1e-12, max_iterations=10, linsolver=ls))
+    curve = C2.continuation_fold(prob, s12.u, s12.p, 6, t2, t2, cpf, bls, symmetric=False, normC=P.norm2, detect_event=2)
+    bts = [sp for sp in curve.specialpoint if sp.type == "bt"]
+    assert len(curve.specialpoint) >= 1 and curve.specialpoint[0].type == "bt" and len(bts) == 1
+    bt = bts[0]
+    assert bt.status == "converged" and bt.interval[0] <= bt.param <= bt.interval[1] and bt.interval[1] - bt.interval[0] < 3e-4
+    assert abs(bt.param - BT_K) < 1e-5 * BT_K                        # the reference's own tolerance
+    assert abs(bt.param - BT_K) < 1e-11, bt.param - BT_K             # ... and in fact the same number
+    assert prob.params == PAR_COM
+    # detect_event = 1: the same crossing recorded without the bisection
+    c1 = C2.continuation_fold(prob, s12.u, s12.p, 6, t2, t2, cpf, bls, symmetric=False, normC=P.norm2, detect_event=1)
+    assert [sp.type for sp in c1.specialpoint] == ["bt"] and c1.specialpoint[0].status == "guess"
+    assert c1.specialpoint[0].interval[0] < 0.9713976 < c1.specialpoint[0].interval[1]
