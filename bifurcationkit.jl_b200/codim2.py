@@ -330,7 +330,7 @@ class FoldCurve:
     p1: list        # the Fold curve (p1[k], p2[k])
     p2: list
     BT: list        # test function <w / ||w||, v / ||v||> at every point: zero at a Bogdanov-Takens point (test_bt_cusp)
-    CP: list        # p1-component of the tangent: zero at a cusp
+    CP: list        # p2-component of the tangent, getp(state.tau) (test_bt_cusp): changes sign at a cusp, where p2 is extremal along the curve
     ma: object
     state: object
     specialpoint: list = None   # Codim2Point entries (detect_event > 0)
@@ -363,7 +363,7 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
 
     def values_at(s):   # test_bt_cusp at a state, the border vectors untouched
         pb._set2(s.z_p)
-        return (ma.update(s.z_u.u, s.z_u.p, keep_borders=True), s.tau_u.p)
+        return (ma.update(s.z_u.u, s.z_u.p, keep_borders=True), s.tau_p)
 
     def cb(st):
         pb._set2(st.z_p)
@@ -371,7 +371,7 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
             ma.update(st.z_u.u, st.z_u.p)
         else:
             ma.update(st.z_u.u, st.z_u.p, keep_borders=True)
-        vals = (ma.BT, st.tau_u.p)
+        vals = (ma.BT, st.tau_p)
         if detect_event > 0 and curve.BT and st.step > 0:
             prev = (curve.BT[-1], curve.CP[-1])
             flips = [k for k in range(2) if (prev[k] > 0) != (vals[k] > 0)]
@@ -381,7 +381,7 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
                     status, interval, lab = locate_event(it, st, values_at, ("bt", "cusp"))
                     label = lab or label
                     pb._set2(st.z_p)
-                    vals = (ma.update(st.z_u.u, st.z_u.p, keep_borders=True), st.tau_u.p)
+                    vals = (ma.update(st.z_u.u, st.z_u.p, keep_borders=True), st.tau_p)
                 if status != "none":
                     curve.specialpoint.append(Codim2Point(label, st.z_p, st.z_u.p, st.step, status, tuple(interval), V.copy(st.z_u.u)))
         curve.p1.append(st.z_u.p)

@@ -1,0 +1,88 @@
+"""Numbers the reference's own test-suite prints for the CO-oxidation model, reproduced by the product's HOST logic (palc.py, events.py,
+codim2.py) with the oracle's dense solvers as the linear-algebra backend -- test/hopf_codim_2/COModel.jl:19-59.
+
+These values are not bifurcation parameters to full precision: they are the END POINTS of the reference's bisections (n_inversion
+halvings of adaptive PALC steps).  They depend on every step length, every Newton iteration count and every reversal along the way,
+so matching them to the printed digits -- and the one 16-digit value to 2e-14 -- pins the arithmetic of the whole host chain against
+the reference itself, which this image cannot run."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from oracle import krylov, bls as obls
+from tests.test_host_logic_cpu import BlsAdapter
+from tests.test_codim2_curves_cpu import NumpyProblem2, COm, COmJ
+
+PAR = [2.5, 1.0, 10.0, 0.0675, 1.0, 0.1, 0.4]                  # par_com, COModel.jl:20
+Z0 = np.array([0.001137, 0.891483, 0.062345])                  # :22
+
+
+def _isapprox(a, b, rtol=np.sqrt(np.finfo(float).eps)):
+    """Julia's isapprox default: |a - b| <= sqrt(eps) max(|a|, |b|)"""
+    return abs(a - b) <= rtol * max(abs(a), abs(b))
+
+
+def _dense_eig(J, nev):
+    vals, vecs = np.linalg.eig(np.asarray(J))
+    o = np.argsort(-vals.real)                                  # decreasing real part (src/EigSolver.jl:16-19)
+    return vals[o][:nev], vecs[:, o][:, :nev], True, 1
+
+
+@pytest.fixture(scope="module")
+def co():
+    bk = g.load_package()
+    return bk, NumpyProblem2(COm, COmJ, Z0.copy(), PAR, 1), krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
+
+
+def test_special_points_of_the_co_branch(co):
+    """COModel.jl:27-34: continuation(prob, PALC(), ContinuationPar(p_min = 0.5, p_max = 2.3, ds = 0.002, dsmax = 0.01, n_inversion = 6,
+    detect_bifurcation = 3, max_bisection_steps = 25, nev = 3, max_steps = 100); normC = norminf, bothside = true):
+    specialpoint[2..5].param ≈ 1.04099606, 1.05220029, 1.04204851, 1.05158367  (Hopf, fold, fold, Hopf; the forward half)."""
+    bk, prob, ls, bls = co
+    P, E = bk.palc, bk.events
+    cp = P.ContinuationPar(p_min=0.5, p_max=2.3, ds=0.002, dsmax=0.01, dsmin=1e-4, max_steps=100, n_inversion=6, max_bisection_steps=25, nev=3,
+                           detect_bifurcation=3, newton_options=P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls, eigsolver=_dense_eig))
+    br = E.continuation(prob, P.PALC(bls=bls), cp, normC=P.norminf)
+    sp = [s for s in br.specialpoint if s.type != "endpoint"]
+    assert [s.type for s in sp] == ["hopf", "bp", "bp", "hopf"] and all(s.status == "converged" for s in sp)
+    for s, gold in zip(sp, (1.04099606, 1.05220029, 1.04204851, 1.05158367)):
+        assert _isapprox(s.param, gold), (s.type, s.param, gold)
+    # none of these is the bifurcation value itself: the Hopf points of the model sit at 1.04099157 and 1.05155746
+    assert abs(sp[0].param - 1.04099157) > 3e-6 and abs(sp[3].param - 1.05155746) > 2e-5
+
+
+def test_special_points_of_the_fold_curve(co):
+    """COModel.jl:36-59: sn_codim2 = continuation(br, 3, (@optic _.k), ContinuationPar(opts_br, p_max = 2.2, p_min = 0., ds = -0.001,
+    dsmax = 0.05, n_inversion = 8, max_steps = 50); normC = norminf, detect_codim2_bifurcation = 2, update_minaug_every_step = 1,
+    bothside = true) with NewtonPar(max_iterations = 10, tol = 1e-12):
+        specialpoint[2] bt   param ≈ 0.97139757 (atol 1e-5),  printsol (k, q2) ≈ (0.971397, 1.417628) rtol 1e-4
+        specialpoint[3] cusp param ≈ 0.35665351 (rtol 1e-4)
+        specialpoint[4] bt   param ≈ 0.7223392465523879,      printsol (k, q2) ≈ (0.722339, 1.161199) rtol 1e-4"""
+    bk, prob, ls, bls = co
+    P, C2 = bk.palc, bk.codim2
+    # the Fold br.specialpoint[3] (q2 = 1.05220029): second turning point of the branch, refined on the minimally augmented system
+    cp = P.ContinuationPar(p_min=0.5, p_max=2.3, ds=0.002, dsmax=0.01, dsmin=1e-4, max_steps=400, newton_options=P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls))
+    pts = []
+    rows, _ = P.continuation(prob, P.PALC(bls=bls), cp, normC=P.norminf, callback=lambda s: pts.append((s.z_u.copy(), s.z_p, s.tau_u.copy())) or True)
+    ps = [r["param"] for r in rows]
+    i = next(k for k in range(1, len(ps) - 1) if ps[k] > ps[k - 1] and ps[k] > ps[k + 1])
+    x0, p0, tau = pts[i]
+    t = tau / np.linalg.norm(tau)
+    nopt = P.NewtonPar(tol=1e-12, max_iterations=10, linsolver=ls)
+    f3 = C2.newton_fold(prob, x0, p0, t, t, nopt, bls, symmetric=False)
+    assert f3.converged and _isapprox(f3.p, 1.05220029)
+    found = []
+    for ds in (-0.001, 0.001):                                   # bothside = true: the two directions from the same Fold point
+        cpf = P.ContinuationPar(p_min=0.0, p_max=2.2, ds=ds, dsmax=0.05, dsmin=1e-4, max_steps=50, n_inversion=8, max_bisection_steps=25, newton_options=nopt)
+        curve = C2.continuation_fold(prob, f3.u, f3.p, 6, t, t, cpf, bls, symmetric=False, normC=P.norminf, detect_event=2)
+        found += curve.specialpoint
+    assert sorted(s.type for s in found) == ["bt", "bt", "cusp"]
+    bt_hi = next(s for s in found if s.type == "bt" and s.param > 0.9)
+    bt_lo = next(s for s in found if s.type == "bt" and s.param < 0.9)
+    cusp = next(s for s in found if s.type == "cusp")
+    assert abs(bt_hi.param - 0.97139757) < 1e-5 and _isapprox(bt_hi.param, 0.971397, 1e-4) and _isapprox(bt_hi.p1, 1.417628, 1e-4)
+    assert _isapprox(cusp.param, 0.35665351, 1e-4)
+    assert _isapprox(bt_lo.param, 0.7223392465523879)            # the reference's assertion (default isapprox) ...
+    assert abs(bt_lo.param - 0.7223392465523879) < 1e-12, bt_lo.param - 0.7223392465523879   # ... and to the last digits
+    assert _isapprox(bt_lo.param, 0.722339, 1e-4) and _isapprox(bt_lo.p1, 1.161199, 1e-4)
+    assert bt_lo.status == bt_hi.status == "converged"
