@@ -86,3 +86,40 @@ def test_special_points_of_the_fold_curve(co):
     assert abs(bt_lo.param - 0.7223392465523879) < 1e-12, bt_lo.param - 0.7223392465523879   # ... and to the last digits
     assert _isapprox(bt_lo.param, 0.722339, 1e-4) and _isapprox(bt_lo.p1, 1.161199, 1e-4)
     assert bt_lo.status == bt_hi.status == "converged"
+
+
+def test_special_point_intervals_of_the_lorenz84_branch():
+    """test/hopf_codim_2/lorenz84.jl:7-65: continuation(prob, PALC(tangent = Bordered()), ContinuationPar(p_min = -1.5, p_max = 3.0,
+    ds = 0.001, dsmax = 0.025, detect_bifurcation = 3, n_inversion = 6, max_bisection_steps = 25, nev = 4, max_steps = 252);
+    normC = norminf, bothside = true) -- the bisection INTERVALS of its four special points, 16 digits each:
+        (2.859863413561998, 2.859897757930758) (2.467211879219629, 2.467246154619121)
+        (1.619657484413436, 1.6196654620692468) (1.546648372620807, 1.5466483727182652)
+    (the half of `bothside` that leaves F = 3 = p_max downwards; the other half has nowhere to go).  Bordered tangent, MatrixBLS."""
+    bk = g.load_package()
+    P, E = bk.palc, bk.events
+
+    def Lor(u, q):
+        al, be, G, de, ga, T, F = q
+        X, Y, Z, U = u
+        return np.array([-Y**2 - Z**2 - al * X + al * F - ga * U**2, X * Y - be * X * Z - Y + G, be * X * Y + X * Z - Z, -de * U + ga * U * X + T])
+
+    def JLor(u, q):
+        al, be, G, de, ga, T, F = q
+        X, Y, Z, U = u
+        return np.array([[-al, -2 * Y, -2 * Z, -2 * ga * U], [Y - be * Z, X - 1, -be * X, 0], [be * Y + Z, be * X, X - 1, 0], [ga * U, 0, 0, -de + ga * X]])
+    par = [0.25, 1.0, 0.25, 1.04, 0.987, 0.04, 3.0]             # (alpha, beta, G, delta, gamma, T, F), :31
+    z0 = np.array([2.9787004394953343, -0.03868302503393752, 0.058232737694740085, -0.02105288273117459])   # :43
+    ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
+    prob = NumpyProblem2(Lor, JLor, z0, par, 6)
+    cp = P.ContinuationPar(p_min=-1.5, p_max=3.0, ds=-0.001, dsmax=0.025, dsmin=1e-4, max_steps=252, n_inversion=6, max_bisection_steps=25, nev=4,
+                           detect_bifurcation=3, newton_options=P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls, eigsolver=_dense_eig))
+    br = E.continuation(prob, P.PALC(tangent="bordered", bls=bls), cp, normC=P.norminf)
+    sp = [s for s in br.specialpoint if s.type != "endpoint"]
+    gold = [(1.546648372620807, 1.5466483727182652), (1.619657484413436, 1.6196654620692468),
+            (2.467211879219629, 2.467246154619121), (2.859863413561998, 2.859897757930758)]
+    assert [s.type for s in sp] == ["bp", "hopf", "hopf", "hopf"]   # the fold of the branch (one real eigenvalue), then three Hopf points
+    for s, (lo, hi) in zip(sp, gold):
+        assert _isapprox(s.interval[0], lo) and _isapprox(s.interval[1], hi), (s.type, s.interval, (lo, hi))   # lorenz84.jl:62-65
+        assert s.status == "converged" and s.interval[0] <= s.param <= s.interval[1]
+    assert abs(sp[0].interval[0] - gold[0][0]) < 1e-12 and abs(sp[0].interval[1] - gold[0][1]) < 1e-12
+    assert br.specialpoint[-1].type == "endpoint" and br.specialpoint[-1].param == 3.0
