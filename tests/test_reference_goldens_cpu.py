@@ -88,6 +88,24 @@ def test_special_points_of_the_fold_curve(co):
     assert bt_lo.status == bt_hi.status == "converged"
 
 
+def Lor(u, q):
+    """test/hopf_codim_2/lorenz84.jl:7-16, q = (alpha, beta, G, delta, gamma, T, F)"""
+    al, be, G, de, ga, T, F = q
+    X, Y, Z, U = u
+    return np.array([-Y**2 - Z**2 - al * X + al * F - ga * U**2, X * Y - be * X * Z - Y + G, be * X * Y + X * Z - Z, -de * U + ga * U * X + T])
+
+
+def JLor(u, q):
+    """:18-27"""
+    al, be, G, de, ga, T, F = q
+    X, Y, Z, U = u
+    return np.array([[-al, -2 * Y, -2 * Z, -2 * ga * U], [Y - be * Z, X - 1, -be * X, 0], [be * Y + Z, be * X, X - 1, 0], [ga * U, 0, 0, -de + ga * X]])
+
+
+PAR_LOR = [0.25, 1.0, 0.25, 1.04, 0.987, 0.04, 3.0]             # (alpha, beta, G, delta, gamma, T, F), :31
+Z0_LOR = np.array([2.9787004394953343, -0.03868302503393752, 0.058232737694740085, -0.02105288273117459])   # :43
+
+
 def test_special_point_intervals_of_the_lorenz84_branch():
     """test/hopf_codim_2/lorenz84.jl:7-65: continuation(prob, PALC(tangent = Bordered()), ContinuationPar(p_min = -1.5, p_max = 3.0,
     ds = 0.001, dsmax = 0.025, detect_bifurcation = 3, n_inversion = 6, max_bisection_steps = 25, nev = 4, max_steps = 252);
@@ -98,19 +116,8 @@ def test_special_point_intervals_of_the_lorenz84_branch():
     bk = g.load_package()
     P, E = bk.palc, bk.events
 
-    def Lor(u, q):
-        al, be, G, de, ga, T, F = q
-        X, Y, Z, U = u
-        return np.array([-Y**2 - Z**2 - al * X + al * F - ga * U**2, X * Y - be * X * Z - Y + G, be * X * Y + X * Z - Z, -de * U + ga * U * X + T])
-
-    def JLor(u, q):
-        al, be, G, de, ga, T, F = q
-        X, Y, Z, U = u
-        return np.array([[-al, -2 * Y, -2 * Z, -2 * ga * U], [Y - be * Z, X - 1, -be * X, 0], [be * Y + Z, be * X, X - 1, 0], [ga * U, 0, 0, -de + ga * X]])
-    par = [0.25, 1.0, 0.25, 1.04, 0.987, 0.04, 3.0]             # (alpha, beta, G, delta, gamma, T, F), :31
-    z0 = np.array([2.9787004394953343, -0.03868302503393752, 0.058232737694740085, -0.02105288273117459])   # :43
     ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
-    prob = NumpyProblem2(Lor, JLor, z0, par, 6)
+    prob = NumpyProblem2(Lor, JLor, Z0_LOR.copy(), PAR_LOR, 6)
     cp = P.ContinuationPar(p_min=-1.5, p_max=3.0, ds=-0.001, dsmax=0.025, dsmin=1e-4, max_steps=252, n_inversion=6, max_bisection_steps=25, nev=4,
                            detect_bifurcation=3, newton_options=P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls, eigsolver=_dense_eig))
     br = E.continuation(prob, P.PALC(tangent="bordered", bls=bls), cp, normC=P.norminf)
@@ -123,3 +130,29 @@ def test_special_point_intervals_of_the_lorenz84_branch():
         assert s.status == "converged" and s.interval[0] <= s.param <= s.interval[1]
     assert abs(sp[0].interval[0] - gold[0][0]) < 1e-12 and abs(sp[0].interval[1] - gold[0][1]) < 1e-12
     assert br.specialpoint[-1].type == "endpoint" and br.specialpoint[-1].param == 3.0
+
+
+def test_bogdanov_takens_points_on_the_lorenz84_fold_curve():
+    """lorenz84.jl:70-84: the Fold br.specialpoint[5] (F = 1.5466) continued in T with ContinuationPar(opts_br, p_max = 3.2, p_min = -0.1,
+    dsmin = 1e-5, ds = -0.001, dsmax = 0.005, max_steps = 60), detect_codim2_bifurcation = 1 (events recorded at the step after the
+    crossing, no bisection): specialpoint[1].param ≈ +0.02058724 and specialpoint[4].param ≈ -0.02135893 (rtol 1e-5) are the two
+    Bogdanov-Takens crossings; the two in between (+0.00004983, -0.00045281) are zero-Hopf / cusp events of the eigenvalue-based test
+    function, which this host logic does not evaluate on Fold curves."""
+    bk = g.load_package()
+    P, C2 = bk.palc, bk.codim2
+    ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
+    prob = NumpyProblem2(Lor, JLor, Z0_LOR.copy(), PAR_LOR, 6)
+    nopt = P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls)
+    cp = P.ContinuationPar(p_min=-1.5, p_max=3.0, ds=-0.001, dsmax=0.025, dsmin=1e-4, max_steps=252, newton_options=nopt)
+    pts = []
+    rows, _ = P.continuation(prob, P.PALC(tangent="bordered", bls=bls), cp, normC=P.norminf,
+                             callback=lambda s: pts.append((s.z_u.copy(), s.z_p, s.tau_u.copy())) or True)
+    i = int(np.argmin([r["param"] for r in rows]))               # the turning point of the branch in F
+    x0, p0, tau = pts[i]
+    t = tau / np.linalg.norm(tau)
+    f = C2.newton_fold(prob, x0, p0, t, t, nopt, bls, symmetric=False)
+    assert f.converged and 1.546648372620807 <= f.p + 1e-9 and f.p - 1e-9 <= 1.5466483727182652   # inside the reference's interval for it
+    cpf = P.ContinuationPar(p_min=-0.1, p_max=3.2, ds=-0.001, dsmax=0.005, dsmin=1e-5, max_steps=60, n_inversion=8, max_bisection_steps=25, newton_options=nopt)
+    curve = C2.continuation_fold(prob, f.u, f.p, 5, t, t, cpf, bls, symmetric=False, normC=P.norminf, detect_event=1)
+    bts = [s for s in curve.specialpoint if s.type == "bt"]
+    assert len(bts) == 2 and _isapprox(bts[0].param, 0.02058724, 1e-5) and _isapprox(bts[1].param, -0.02135893, 1e-5), [s.param for s in bts]
