@@ -336,8 +336,18 @@ class FoldCurve:
     specialpoint: list = None   # Codim2Point entries (detect_event > 0)
 
 
+def test_zh(eigvals, tol_stability):
+    """test_zh (MinAugFold.jl:533-543): Zero-Hopf test function on a Fold curve -- the number of eigenvalues of J(x, p) to the right
+    of the (numerically) zero one with a positive imaginary part; a change between two points is a "zh" event"""
+    if eigvals is None:
+        return 1
+    ev = np.asarray(eigvals)
+    rho = float(np.min(np.abs(ev.real)))
+    return int(np.sum((ev.real > rho) & (ev.imag > tol_stability)))
+
+
 def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls, alg=None, normC=V.norminf, symmetric=True,
-                      update_minaug_every_step=1, record=None, callback=None, detect_event=0):
+                      update_minaug_every_step=1, record=None, callback=None, detect_event=0, eigsolver=None):
     """Codim-2 continuation of a Fold point in the parameters (p1 = params[prob.lens], p2 = params[lens2]):
     continuation_fold(prob, alg, foldpointguess, par, lens1, lens2, eigenvec, eigenvec_ad, options_cont; jacobian_ma = MinAug())
     (MinAugFold.jl:366-452).  PALC on the minimally augmented system, Newton linear solver = FoldLinearSolverMinAug over the
@@ -346,7 +356,8 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
     Bogdanov-Takens and cusp test functions recorded along the curve.  detect_event = 1: a change of sign of a test function
     between two points is recorded as a special point ("bt" / "cusp", the event of :428-431); = 2: it is located by the reference's
     bisection (locate_event) with contpar.n_inversion / max_bisection_steps / dsmin_bisection, and the curve goes on from the
-    located state, as in the reference."""
+    located state, as in the reference.  eigsolver (J, nev) -> (eigenvalues, ...): eigenvalues of J along the curve (FoldEig, :577-590;
+    contpar.nev of them) for the Zero-Hopf event "zh" (DiscreteEvent(1, test_zh), :431; recorded at the point after the change)."""
     from . import palc as P
     ma = FoldMinAug(prob, eigenvec_ad, eigenvec, bls, symmetric=symmetric, norm=normC)
     z0 = BorderedVec(V.copy(x0), p1_0)
@@ -360,6 +371,7 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
     curve = FoldCurve([], [], [], [], [], ma, None, [])
     from . import events as E
     it = E._Iter(pb, alg, cp, normC)
+    zh_hist = []
 
     def values_at(s):   # test_bt_cusp at a state, the border vectors untouched
         pb._set2(s.z_p)
@@ -372,6 +384,12 @@ def continuation_fold(prob, x0, p1_0, lens2, eigenvec, eigenvec_ad, contpar, bls
         else:
             ma.update(st.z_u.u, st.z_u.p, keep_borders=True)
         vals = (ma.BT, st.tau_p)
+        if eigsolver is not None:
+            zh = test_zh(eigsolver(prob.J(st.z_u.u, st.z_u.p), contpar.nev)[0], contpar.tol_stability)
+            if detect_event > 0 and zh_hist and st.step > 0 and zh != zh_hist[-1]:
+                curve.specialpoint.append(Codim2Point("zh", st.z_p, st.z_u.p, st.step, "guess", tuple(E.getinterval(curve.p2[-1], st.z_p)),
+                                                      V.copy(st.z_u.u)))
+            zh_hist.append(zh)
         if detect_event > 0 and curve.BT and st.step > 0:
             prev = (curve.BT[-1], curve.CP[-1])
             flips = [k for k in range(2) if (prev[k] > 0) != (vals[k] > 0)]

@@ -132,12 +132,12 @@ def test_special_point_intervals_of_the_lorenz84_branch():
     assert br.specialpoint[-1].type == "endpoint" and br.specialpoint[-1].param == 3.0
 
 
-def test_bogdanov_takens_points_on_the_lorenz84_fold_curve():
+def test_special_points_of_the_lorenz84_fold_curve():
     """lorenz84.jl:70-84: the Fold br.specialpoint[5] (F = 1.5466) continued in T with ContinuationPar(opts_br, p_max = 3.2, p_min = -0.1,
-    dsmin = 1e-5, ds = -0.001, dsmax = 0.005, max_steps = 60), detect_codim2_bifurcation = 1 (events recorded at the step after the
-    crossing, no bisection): specialpoint[1].param ≈ +0.02058724 and specialpoint[4].param ≈ -0.02135893 (rtol 1e-5) are the two
-    Bogdanov-Takens crossings; the two in between (+0.00004983, -0.00045281) are zero-Hopf / cusp events of the eigenvalue-based test
-    function, which this host logic does not evaluate on Fold curves."""
+    detect_bifurcation = 1, dsmin = 1e-5, ds = -0.001, dsmax = 0.005, max_steps = 60), detect_codim2_bifurcation = 1 (events recorded at
+    the point after the change, no bisection):
+        specialpoint[1..4].param ≈ +0.02058724 (rtol 1e-5), +0.00004983 (atol 1e-8), -0.00045281 (rtol 1e-5), -0.02135893 (rtol 1e-5)
+    -- Bogdanov-Takens, Zero-Hopf, Zero-Hopf, Bogdanov-Takens: step points of the adaptive PALC run on the minimally augmented system."""
     bk = g.load_package()
     P, C2 = bk.palc, bk.codim2
     ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
@@ -152,7 +152,10 @@ def test_bogdanov_takens_points_on_the_lorenz84_fold_curve():
     t = tau / np.linalg.norm(tau)
     f = C2.newton_fold(prob, x0, p0, t, t, nopt, bls, symmetric=False)
     assert f.converged and 1.546648372620807 <= f.p + 1e-9 and f.p - 1e-9 <= 1.5466483727182652   # inside the reference's interval for it
-    cpf = P.ContinuationPar(p_min=-0.1, p_max=3.2, ds=-0.001, dsmax=0.005, dsmin=1e-5, max_steps=60, n_inversion=8, max_bisection_steps=25, newton_options=nopt)
-    curve = C2.continuation_fold(prob, f.u, f.p, 5, t, t, cpf, bls, symmetric=False, normC=P.norminf, detect_event=1)
-    bts = [s for s in curve.specialpoint if s.type == "bt"]
-    assert len(bts) == 2 and _isapprox(bts[0].param, 0.02058724, 1e-5) and _isapprox(bts[1].param, -0.02135893, 1e-5), [s.param for s in bts]
+    cpf = P.ContinuationPar(p_min=-0.1, p_max=3.2, ds=-0.001, dsmax=0.005, dsmin=1e-5, max_steps=60, n_inversion=8, max_bisection_steps=25, nev=4,
+                            newton_options=nopt)
+    curve = C2.continuation_fold(prob, f.u, f.p, 5, t, t, cpf, bls, symmetric=False, normC=P.norminf, detect_event=1, eigsolver=_dense_eig)
+    sp = curve.specialpoint
+    assert [s.type for s in sp] == ["bt", "zh", "zh", "bt"], [(s.type, s.param) for s in sp]
+    assert _isapprox(sp[0].param, 0.02058724, 1e-5) and abs(sp[1].param - 0.00004983) < 1e-8
+    assert _isapprox(sp[2].param, -0.00045281, 1e-5) and _isapprox(sp[3].param, -0.02135893, 1e-5)
