@@ -269,7 +269,7 @@ class Codim2Point:
     x: object
 
 
-def locate_event(it, _st, values_at, labels):
+def locate_event(it, _st, values_at, labels, indicator=None):
     """locate_event!(event, iter, state) (src/events/EventDetection.jl:28-235) for a ContinuousEvent whose indicator is the number of
     positive test functions (nb_signs): bisection on ds from the state `_st` just AFTER the event -- first half a step back, then
     halving, reversing at every change of the indicator -- until contpar.n_inversion reversals (or max_bisection_steps /
@@ -278,8 +278,8 @@ def locate_event(it, _st, values_at, labels):
     from . import events as E
     from .palc import _predict
     cp = it.contpar
-    nb = lambda vals: sum(1 for v in vals if v > 0)
-    if abs(_st.ds) < cp.dsmin:
+    nb = indicator or (lambda vals: sum(1 for v in vals if v > 0))   # nb_signs: ContinuousEvent -> number of positive values;
+    if abs(_st.ds) < cp.dsmin:                                         # DiscreteEvent -> the value itself (EventDetection.jl:2-3)
         return "none", (0.0, 0.0), None
     v_after = values_at(_st)
     after, st, before = E.copy_state(_st), E.copy_state(_st), E.copy_state(_st)
@@ -304,7 +304,7 @@ def locate_event(it, _st, values_at, labels):
             st.ds /= -2                       # passed it: reverse
             n_inversion += 1
             indinterval = 1 - indinterval
-            changed = [k for k, (a_, b_) in enumerate(zip(prev, vals)) if (a_ > 0) != (b_ > 0)]
+            changed = [k for k, (a_, b_) in enumerate(zip(prev, vals)) if ((a_ > 0) != (b_ > 0) if indicator is None else a_ != b_)]
         _predict(st)
         E.copyto_state(after if n_inversion % 2 == 0 else before, st)
         if st.step > 0:
@@ -321,7 +321,7 @@ def locate_event(it, _st, values_at, labels):
     _st.z_p, _st.zold_p, _st.tau_p, _st.zpred_p = src.z_p, src.zold_p, src.tau_p, src.zpred_p
     _st.work_newton, _st.work_linear = st.work_newton, st.work_linear
     _predict(_st)                             # update_predictor!(_state, iter) with the outer ds
-    return status, E.getinterval(*interval), (labels[changed[0]] if changed else None)
+    return status, E.getinterval(*interval), (labels[min(changed[0], len(labels) - 1)] if changed else None)
 
 
 @dataclass
@@ -460,14 +460,20 @@ class HopfMinAug:
     """[F(x, p); Re sigma; Im sigma](x, p, omega) with  [J - i omega, a; b^H, 0] [v; sigma] = [0; 1]
     (a ~ null vector of (J - i omega)^H, b ~ null vector of J - i omega)."""
 
-    def __init__(self, prob, cprob, a, b, ls, cls):
-        self.prob, self.cprob, self.ls, self.cls = prob, cprob, ls, cls
+    def __init__(self, prob, cprob, a, b, ls, cls, cbls=None):
+        self.prob, self.cprob, self.ls, self.cls, self.cbls = prob, cprob, ls, cls, cbls
         self.a, self.b = np.array(a, dtype=complex), np.array(b, dtype=complex)
         self.itlinear = 0
 
     def _border(self, Jc, shift, a, b):
-        """(Jc + shift) v + a sigma = 0, <b, v> = 1 by bordering: with y = (Jc + shift)^-1 a, sigma = -1 / <b, y>, v = -sigma y
-        (linbdsolver(J, a, b, 0, zero, 1; shift), MinAugHopf.jl:17)"""
+        """(Jc + shift) v + a sigma = 0, <b, v> = 1 (linbdsolver(J, a, b, 0, zero, 1; shift), MinAugHopf.jl:17).  With a complex
+        bordered solver `cbls(Jc, a, b, shift) -> (v, sigma, converged, iters)` (the reference's MatrixBLS / BorderingBLS on the
+        bordered matrix, regular AT the Hopf point) that is one call; otherwise by bordering: y = (Jc + shift)^-1 a,
+        sigma = -1 / <b, y>, v = -sigma y -- fine for an iterative solver next to the point, singular exactly on it."""
+        if self.cbls is not None:
+            v, sigma, cv, it = self.cbls(Jc, a, b, shift)
+            self.itlinear += int(np.sum(it))
+            return v, sigma
         y, cv, it = self.cls(Jc, a, a0=shift)
         self.itlinear += int(np.sum(it))
         sigma = -1.0 / np.vdot(b, y)
@@ -511,10 +517,10 @@ class HopfMinAug:
         return x1, float(dp), float(dom), cv
 
 
-def newton_hopf(prob, cprob, x0, p0, omega0, eigenvec, eigenvec_ad, opts, ls, cls, normN=V.norm2):
+def newton_hopf(prob, cprob, x0, p0, omega0, eigenvec, eigenvec_ad, opts, ls, cls, normN=V.norm2, cbls=None):
     """Newton on the Hopf MA system from (x0, p0, omega0) with guesses for the i omega eigenvector and its adjoint
     (newton_hopf, MinAugHopf.jl:258-283 + src/Newton.jl:66-114 on the state (x, [p, omega]))."""
-    ma = HopfMinAug(prob, cprob, eigenvec_ad, eigenvec, ls, cls)
+    ma = HopfMinAug(prob, cprob, eigenvec_ad, eigenvec, ls, cls, cbls)
     x, p, om = V.copy(x0), float(p0), float(omega0)
     F, sr, si = ma.residual(x, p, om)
     res = math.sqrt(normN(F) ** 2 + sr * sr + si * si)
@@ -587,18 +593,23 @@ class HopfCurve:
     ma: object
     state: object
     stopped_at_bt: bool = False
+    specialpoint: list = None   # Codim2Point entries: "zh" / "hh" (detect_event > 0 with an eigsolver)
 
 
 def continuation_hopf(prob, cprob, x0, p1_0, omega0, lens2, eigenvec, eigenvec_ad, contpar, ls, cls, alg=None, normC=V.norminf,
-                      update_minaug_every_step=1, record=None, callback=None):
+                      update_minaug_every_step=1, record=None, callback=None, cbls=None, detect_event=0, eigsolver=None):
     """Codim-2 continuation of a Hopf point in (p1 = params[prob.lens], p2 = params[lens2]): continuation_hopf(prob, alg,
     hopfpointguess, par, lens1, lens2, eigenvec, eigenvec_ad, options_cont; jacobian_ma = MinAug()) (MinAugHopf.jl:425-522).
     PALC on the minimally augmented system in the state (x, [p1, omega]); Newton linear solver = HopfLinearSolverMinAug (one
     two-right-hand-side real solve + four complex shifted solves on the BK_COMPLEX twin `cprob`), outer bordered solver =
     BorderingBLS(that solver, check_precision = false); after every accepted step a <- w / ||w||, b <- v / ||v|| (update!,
-    :323-367); the curve stops where omega -> 0 (Bogdanov-Takens, |omega| < 100 Newton tol)."""
+    :323-367); the curve stops where omega -> 0 (Bogdanov-Takens, |omega| < 100 Newton tol).  With eigsolver (J, nev) -> (eigenvalues,
+    ...) and detect_event > 0 the number of unstable eigenvalues of J along the curve is the reference's BifDetectEvent (:489-500,
+    src/events/BifurcationDetection.jl:57-70; tol_stability raised to 10 x the Newton tolerance so that the Hopf pair itself does not
+    count): a change is a Zero-Hopf ("zh", one real eigenvalue) or Hopf-Hopf ("hh", a second pair) point, recorded (1) or located by
+    the event bisection (2).  The Bautin test function (first Lyapunov coefficient) needs normal forms and is not evaluated."""
     from . import palc as P
-    ma = HopfMinAug(prob, cprob, eigenvec_ad, eigenvec, ls, cls)
+    ma = HopfMinAug(prob, cprob, eigenvec_ad, eigenvec, ls, cls, cbls)
     z0 = BorderedVec(V.copy(x0), [p1_0, omega0])
     pb = HopfMAProblem(ma, lens2, z0, record)
     hls = HopfLinearSolverMinAug()
@@ -608,11 +619,35 @@ def continuation_hopf(prob, cprob, x0, p1_0, omega0, lens2, eigenvec, eigenvec_a
     alg = alg or P.PALC()
     alg = P.PALC(tangent=alg.tangent, theta=alg.theta, bls=BorderingBLSHost(hls))
     curve = HopfCurve([], [], [], [], ma, None)
+    curve.specialpoint = []
     cnorm = lambda z: float(np.max(np.abs(z)))
+    from . import events as E
+    it = E._Iter(pb, alg, cp, normC)
+    tol_st = max(10 * no.tol, contpar.tol_stability)
+    nhist = []
+
+    def unstable_at(s):   # (n_unstable, n_imag) of J at the Hopf point of state s (is_stable, src/Bifurcations.jl:5-18)
+        pb._set2(s.z_p)
+        ev = np.asarray(eigsolver(prob.J(s.z_u.u, float(s.z_u.p[0])), contpar.nev)[0])
+        un = ev.real > tol_st
+        return (int(np.sum(un)), int(np.sum(un & (np.abs(ev.imag) > tol_st))))
 
     def cb(st):
         pb._set2(st.z_p)
         x, p1, om = st.z_u.u, float(st.z_u.p[0]), float(st.z_u.p[1])
+        if eigsolver is not None:
+            nu = unstable_at(st)
+            if detect_event > 0 and nhist and st.step > 0 and nu[0] != nhist[-1][0]:
+                prev, status, interval = nhist[-1], "guess", E.getinterval(curve.p2[-1], st.z_p)
+                if detect_event > 1:
+                    status, interval, _ = locate_event(it, st, lambda s: (unstable_at(s)[0],), ("hh",), indicator=lambda v: v[0])
+                    pb._set2(st.z_p)
+                    nu = unstable_at(st)
+                    x, p1, om = st.z_u.u, float(st.z_u.p[0]), float(st.z_u.p[1])
+                if status != "none":
+                    dn, di = abs(nu[0] - prev[0]), abs(nu[1] - prev[1])
+                    curve.specialpoint.append(Codim2Point("zh" if dn == 1 else ("hh" if di == 2 else "nd"), st.z_p, p1, st.step, status, tuple(interval), V.copy(x)))
+            nhist.append(nu)
         if st.step % update_minaug_every_step == 0:
             v, _ = ma._border(cprob.J(x, p1), complex(0.0, -om), ma.a, ma.b)
             w, _ = ma._border(cprob.J(x, p1, transpose=True), complex(0.0, om), ma.b, ma.a)

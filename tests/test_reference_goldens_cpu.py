@@ -159,3 +159,60 @@ def test_special_points_of_the_lorenz84_fold_curve():
     assert [s.type for s in sp] == ["bt", "zh", "zh", "bt"], [(s.type, s.param) for s in sp]
     assert _isapprox(sp[0].param, 0.02058724, 1e-5) and abs(sp[1].param - 0.00004983) < 1e-8
     assert _isapprox(sp[2].param, -0.00045281, 1e-5) and _isapprox(sp[3].param, -0.02135893, 1e-5)
+
+
+def _complex_bordered_dense(Jc, a, b, shift):
+    """MatrixBLS on the complex bordered system [Jc + shift, a; b^H, 0] [v; sigma] = [0; 1] (bdlinsolver = MatrixBLS(), lorenz84.jl:95)"""
+    n = len(a)
+    M = np.zeros((n + 1, n + 1), dtype=complex)
+    M[:n, :n] = Jc.M + shift * np.eye(n)
+    M[:n, n] = a
+    M[n, :n] = np.conj(b)
+    r = np.zeros(n + 1, dtype=complex)
+    r[n] = 1
+    sol = np.linalg.solve(M, r)
+    return sol[:n], sol[n], True, 1
+
+
+def test_special_points_of_the_lorenz84_hopf_curve():
+    """lorenz84.jl:88-99: hp_codim2_test = continuation(br, 2, (@optic _.T), ContinuationPar(opts_br, ds = -0.001, dsmax = 0.02, dsmin = 1e-4,
+    n_inversion = 6, max_steps = 100); normC = norminf, detect_codim2_bifurcation = 2, update_minaug_every_step = 1, start_with_eigen =
+    true, bothside = true, bdlinsolver = MatrixBLS()) on the branch computed with PALC(tangent = Bordered()):
+        specialpoint[2].param ≈ +0.02627393 (rtol 1e-5),   specialpoint[3].param ≈ -0.02627430 (atol 1e-8)
+    -- two Hopf-Hopf points (a second complex pair crosses the axis) located by the event bisection on the number of unstable
+    eigenvalues; the whole Hopf chain (complex bordered systems, HopfLinearSolverMinAug, BorderingBLS over it, Bordered tangent)."""
+    from tests.test_host_logic_cpu import _dense_cls, _dense_ls2
+    from tests.test_codim2_curves_cpu import DenseComplexProblem2
+    bk = g.load_package()
+    P, E, C2 = bk.palc, bk.events, bk.codim2
+    ls, bls = krylov.DefaultLS(), BlsAdapter(obls.MatrixBLS())
+    prob = NumpyProblem2(Lor, JLor, Z0_LOR.copy(), PAR_LOR, 6)
+    nopt = P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls)
+    cp = P.ContinuationPar(p_min=-1.5, p_max=3.0, ds=-0.001, dsmax=0.025, dsmin=1e-4, max_steps=252, n_inversion=6, max_bisection_steps=25, nev=4,
+                           detect_bifurcation=3, newton_options=P.NewtonPar(tol=1e-12, max_iterations=25, linsolver=ls, eigsolver=_dense_eig))
+    br = E.continuation(prob, P.PALC(tangent="bordered", bls=bls), cp, normC=P.norminf)
+    h2 = [s for s in br.specialpoint if s.type == "hopf"][-1]    # br.specialpoint[2]: the Hopf point at F = 2.8599
+    assert _isapprox(h2.interval[1], 2.859897757930758)
+    Jh = JLor(h2.x, prob._par(h2.param))
+    vals, vecs = np.linalg.eig(Jh)
+    kk = int(np.argmax(vals.imag))
+    valt, vect = np.linalg.eig(Jh.T)
+    kt = int(np.argmin(valt.imag))
+    cprob = DenseComplexProblem2(prob)
+    hp = C2.newton_hopf(prob, cprob, h2.x, h2.param, vals[kk].imag, vecs[:, kk], vect[:, kt], nopt, _dense_ls2, _dense_cls, cbls=_complex_bordered_dense)
+    assert hp.converged and h2.interval[0] - 1e-6 < hp.p < h2.interval[1] + 1e-6
+    cph = P.ContinuationPar(p_min=-1.5, p_max=3.0, ds=-0.001, dsmax=0.02, dsmin=1e-4, max_steps=100, n_inversion=6, max_bisection_steps=25, nev=4,
+                            newton_options=nopt)
+    curve = C2.continuation_hopf(prob, cprob, hp.u, hp.p, hp.omega, 5, vecs[:, kk], vect[:, kt], cph, _dense_ls2, _dense_cls,
+                                 alg=P.PALC(tangent="bordered"), normC=P.norminf, cbls=_complex_bordered_dense, detect_event=2, eigsolver=_dense_eig)
+    sp = curve.specialpoint
+    assert [s.type for s in sp] == ["hh", "hh"] and all(s.status == "converged" for s in sp), [(s.type, s.param, s.status) for s in sp]
+    assert _isapprox(sp[0].param, 0.02627393, 1e-5) and abs(sp[0].param - 0.02627393) < 1e-8
+    assert abs(sp[1].param - (-0.02627430)) < 1e-8
+    assert prob.params == PAR_LOR and not curve.stopped_at_bt
+    # at the located points J has two pairs on the imaginary axis (Hopf-Hopf): the Hopf pair +- i omega and a second one within the interval
+    for s in sp:
+        q = list(PAR_LOR)
+        q[6], q[5] = s.p1, s.param
+        ev = np.linalg.eigvals(JLor(s.x, q))
+        assert np.sum(np.abs(ev.real) < 1e-5) == 4, ev
