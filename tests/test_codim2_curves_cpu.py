@@ -491,7 +491,7 @@ def test_bogdanov_takens_point_located_as_in_the_reference(com_fold):
     bt = bts[0]
     assert bt.status == "converged" and bt.interval[0] <= bt.param <= bt.interval[1] and bt.interval[1] - bt.interval[0] < 3e-4
     assert abs(bt.param - BT_K) < 1e-5 * BT_K                        # the reference's own tolerance
-    assert abs(bt.param - BT_K) < 1e-11, bt.param - BT_K             # ... and in fact the same number
+    assert abs(bt.param - BT_K) < 1e-9, bt.param - BT_K              # ... and in fact the same number (4e-13 on this host)
     assert prob.params == PAR_COM
     # detect_event = 1: the same crossing recorded without the bisection
     c1 = C2.continuation_fold(prob, s12.u, s12.p, 6, t2, t2, cpf, bls, symmetric=False, normC=P.norm2, detect_event=1)

@@ -83,7 +83,7 @@ def test_special_points_of_the_fold_curve(co):
     assert abs(bt_hi.param - 0.97139757) < 1e-5 and _isapprox(bt_hi.param, 0.971397, 1e-4) and _isapprox(bt_hi.p1, 1.417628, 1e-4)
     assert _isapprox(cusp.param, 0.35665351, 1e-4)
     assert _isapprox(bt_lo.param, 0.7223392465523879)            # the reference's assertion (default isapprox) ...
-    assert abs(bt_lo.param - 0.7223392465523879) < 1e-12, bt_lo.param - 0.7223392465523879   # ... and to the last digits
+    assert abs(bt_lo.param - 0.7223392465523879) < 1e-9, bt_lo.param - 0.7223392465523879    # ... and far inside it (2e-14 on this host)
     assert _isapprox(bt_lo.param, 0.722339, 1e-4) and _isapprox(bt_lo.p1, 1.161199, 1e-4)
     assert bt_lo.status == bt_hi.status == "converged"
 
@@ -128,7 +128,7 @@ def test_special_point_intervals_of_the_lorenz84_branch():
     for s, (lo, hi) in zip(sp, gold):
         assert _isapprox(s.interval[0], lo) and _isapprox(s.interval[1], hi), (s.type, s.interval, (lo, hi))   # lorenz84.jl:62-65
         assert s.status == "converged" and s.interval[0] <= s.param <= s.interval[1]
-    assert abs(sp[0].interval[0] - gold[0][0]) < 1e-12 and abs(sp[0].interval[1] - gold[0][1]) < 1e-12
+    assert abs(sp[0].interval[0] - gold[0][0]) < 1e-9 and abs(sp[0].interval[1] - gold[0][1]) < 1e-9   # 1e-13 on this host
     assert br.specialpoint[-1].type == "endpoint" and br.specialpoint[-1].param == 3.0
 
 
