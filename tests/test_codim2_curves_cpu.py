@@ -497,3 +497,90 @@ def test_bogdanov_takens_point_located_as_in_the_reference(com_fold):
     c1 = C2.continuation_fold(prob, s12.u, s12.p, 6, t2, t2, cpf, bls, symmetric=False, normC=P.norm2, detect_event=1)
     assert [sp.type for sp in c1.specialpoint] == ["bt"] and c1.specialpoint[0].status == "guess"
     assert c1.specialpoint[0].interval[0] < 0.9713976 < c1.specialpoint[0].interval[1]
+
+
+# ------------------------------------------------------------------------------------------------ object vectors (the device code path)
+class ObjVec:
+    """Host stand-in with the method set of core.DeviceVec: codim2 / palc see "a vector that carries its own algebra" exactly as on the
+    device (palc._obj), so the object-vector branches of BorderedVec and of the curve drivers run in the CPU suite too."""
+
+    def __init__(self, a):
+        self.a = np.array(a, dtype=float)
+
+    def __len__(self):
+        return len(self.a)
+
+    def numpy(self):
+        return self.a.copy()
+
+    def copy(self):
+        return ObjVec(self.a)
+
+    def copyto(self, src):
+        self.a[...] = src.a
+        return self
+
+    def zero_(self):
+        self.a[...] = 0.0
+        return self
+
+    def scale_(self, s):
+        self.a *= s
+        return self
+
+    def axpby_(self, a, x, b=1.0):
+        self.a = a * x.a + b * self.a
+        return self
+
+    def dot(self, y):
+        return float(self.a @ y.a)
+
+    def norm(self):
+        return float(np.linalg.norm(self.a))
+
+    def norminf(self):
+        return float(np.max(np.abs(self.a)))
+
+    def diffdot(self, x0, tau):
+        return float((self.a - x0.a) @ tau.a)
+
+
+class ObjProblem2(NumpyProblem2):
+    """NumpyProblem2 whose state vectors are ObjVec"""
+
+    def F(self, x, p, out=None):
+        r = ObjVec(self.F_(x.a, self._par(p)))
+        return r if out is None else out.copyto(r)
+
+    def J(self, x, p):
+        return self.J_(x.a, self._par(p))
+
+    def Jt(self, x, p):
+        return self.J_(x.a, self._par(p)).T
+
+
+class ObjBls:
+    """bordered solver on ObjVec through the oracle's dense MatrixBLS; a Jacobian applied to an ObjVec returns an ObjVec"""
+
+    def __init__(self):
+        self.inner = BlsAdapter(obls.MatrixBLS())
+
+    def __call__(self, J, dR, dzu, dzp, R, n, xiu=1.0, xip=1.0, shift=None, dotscale=1.0):
+        u, up, ok, it = self.inner(J, dR.a, dzu.a, dzp, R.a, n, xiu, xip, shift=shift, dotscale=dotscale)
+        return ObjVec(u), up, ok, it
+
+
+def test_fold_curve_on_object_vectors_matches_the_array_run(com_fold, monkeypatch):
+    """the CO Fold curve with event location, once on ndarrays and once on DeviceVec-like objects: same points, same special point"""
+    bk, prob, ls, bls, sol, t = com_fold
+    P, C2 = bk.palc, bk.codim2
+    monkeypatch.setattr(C2, "_apply", lambda J, v: ObjVec(J @ v.a) if isinstance(v, ObjVec) else (J(v) if callable(J) else J @ v))
+    cpf = P.ContinuationPar(p_min=0.0, p_max=1.0, ds=0.002, dsmax=0.01, dsmin=1e-4, max_steps=50, n_inversion=4, max_bisection_steps=25,
+                            newton_options=P.NewtonPar(tol=1e-12, max_iterations=10, linsolver=ls))
+    ref = C2.continuation_fold(prob, sol.u, sol.p, 6, t, t, cpf, bls, symmetric=False, normC=P.norm2, detect_event=2)
+    oprob = ObjProblem2(COm, COmJ, ObjVec(prob.u0), PAR_COM, 1)
+    cur = C2.continuation_fold(oprob, ObjVec(sol.u), sol.p, 6, ObjVec(t), ObjVec(t), cpf, ObjBls(), symmetric=False, normC=P.norm2, detect_event=2)
+    assert len(cur.rows) == len(ref.rows) and np.allclose(cur.p1, ref.p1, rtol=0, atol=1e-12) and np.allclose(cur.p2, ref.p2, rtol=0, atol=1e-12)
+    assert [s.type for s in cur.specialpoint] == [s.type for s in ref.specialpoint] == ["bt"]
+    assert abs(cur.specialpoint[0].param - ref.specialpoint[0].param) < 1e-12 and isinstance(cur.specialpoint[0].x, ObjVec)
+    assert isinstance(cur.state.z_u.u, ObjVec) and oprob.params == PAR_COM
