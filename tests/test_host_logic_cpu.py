@@ -642,3 +642,59 @@ def test_bothside_two_ranks_gloo():
     single, _ = bk.segments.continuation_bothside(P, mk, alg, cp, P.norm2)
     assert res[0][1] == res[1][1] and np.array_equal(np.array(res[0][1]), single)
     assert res[0][3] > 0.2 and res[1][3] < 0.2 and res[0][2] + res[1][2] == len(single)   # rank 0 went up, rank 1 down
+
+
+# ------------------------------------------------------------------------------------------------ speculative step sizes (a multi-rank run of ONE branch)
+def _spec_setup(bk):
+    """r + x - x^3 from the upper branch with a corrector that often fails (3 Newton iterations, large steps): many rejected steps"""
+    P = bk.palc
+    F = lambda x, r: r + x - x**3
+    J = lambda x, r: np.diag(1 - 3 * x**2)
+    ls = krylov.DefaultLS()
+    cp = P.ContinuationPar(dsmin=0.002, dsmax=0.6, ds=-0.4, p_max=4.1, p_min=-1.0, max_steps=40, a=1.0,
+                           newton_options=P.NewtonPar(tol=1e-10, max_iterations=3, linsolver=ls))
+    mk = lambda: NumpyProblem(F, J, np.array([1.3247179572447460]), 1.0, record=lambda x: x[0])
+    return P, mk, P.PALC(bls=BlsAdapter(obls.MatrixBLS())), cp
+
+
+def _spec_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as gg
+    bk = gg.load_package()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, mk, alg, cp = _spec_setup(bk)
+    rows, st, info = bk.segments.continuation_speculative(P, mk(), alg, cp, P.norm2, dist, torch, "cpu")
+    q.put((rank, [[r[k] for k in ("param", "x", "itnewton", "itlinear", "ds", "step")] for r in rows], st.nfail, st.work_newton, st.stop, info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_speculative_step_sizes_reproduce_the_sequential_branch(world):
+    """segments.continuation_speculative on `world` gloo ranks: rows, rejected-step count, corrector work and the stop flag equal the
+    single-process palc.continuation exactly; the rejected attempts no longer cost rounds."""
+    import torch.multiprocessing as mp
+    bk = g.load_package()
+    P, mk, alg, cp = _spec_setup(bk)
+    ref, st = P.continuation(mk(), alg, cp)
+    assert st.nfail >= 2                                              # the setup does reject steps
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + world
+    ps = [ctx.Process(target=_spec_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[r[k] for k in ("param", "x", "itnewton", "itlinear", "ds", "step")] for r in ref]
+    for rank, rows, nfail, wn, stop, info in res:
+        assert rows == want, (rank, len(rows), len(want))               # bit for bit
+        assert nfail == st.nfail and wn == st.work_newton and stop == st.stop
+        assert info["attempts"] == st.nfail + st.step                   # every attempt of the sequential loop, rejected or accepted
+        assert info["rounds"] < info["attempts"]                        # at least one rejection was absorbed by a speculative rank
+    assert res[0][5] == res[-1][5]
