@@ -335,7 +335,7 @@ TIMING_EVERY = 8  # roofline sampling: the event records sit between PDL launche
 SCOUT = dict(ds_factor=4.0, newton_tol=1e-4, newton_maxit=8, gmres_reltol=1e-2)  # seed generator of the N > 1 partition (tools/scout_probe.py)
 
 
-def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timing=True, wrap=None, nsteps=None):
+def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timing=True, wrap=None, nsteps=None, spec=None):
     """One rank's job.  world == 1 (also every rank of the default "replicas" mode): exactly `nsteps` continuation steps from
     u_start; world > 1: this rank's chunk of the arclength window s_total (--partition scout).  Returns (rows, ms, stats delta, info)."""
     P, S = bk.palc, bk.segments
@@ -348,7 +348,16 @@ def window_job(bk, ctx, ls, n, u_start, s_total, rank, world, torch, flush, timi
     s0 = ctx.stats()
     torch.cuda.profiler.start()
     info = {"scout_ms": 0.0, "scout_points": 0, "chunk": None, "rejected": 0, "work_newton": 0, "work_linear": 0}
-    if world == 1:
+    if spec is not None:
+        # --partition speculative: ONE branch on all ranks, rank r correcting with the r-times-halved step (segments.continuation_speculative);
+        # spec = (dist, device).  Rows equal the 1-GPU rows; the collectives are an all_gather of 4 doubles and a broadcast of the accepted
+        # point per step, both inside the timed region.
+        cp1 = cpf()
+        cp1.max_steps = nsteps
+        rows, st, sinfo = S.continuation_speculative(P, mkprob(u_start, PAR[0]), alg, cp1, P.norminf, spec[0], torch, spec[1], callback=tm.wrap(None))
+        rows = rows[: nsteps + 1]
+        info["speculative"] = sinfo
+    elif world == 1:
         cp1 = cpf()
         cp1.max_steps = nsteps
         rows, st = P.continuation(mkprob(u_start, PAR[0]), alg, cp1, normC=P.norminf, callback=tm.wrap(None))
@@ -410,7 +419,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bls", default="matrixfree", choices=["matrixfree", "bordering"])
     ap.add_argument("--branch", default="front", choices=["front", "hexagons"])
-    ap.add_argument("--partition", default="replicas", choices=["replicas", "scout"], help="N > 1: independent branches (default) or one window cut by a scout")
+    ap.add_argument("--partition", default="replicas", choices=["replicas", "scout", "speculative"],
+                    help="N > 1: independent replicas (default), one window cut by a scout, or one branch with speculative step sizes (not measured on GPUs yet)")
     args = ap.parse_args()
     n, K, B = args.grid, args.steps, args.batch
     BLS["kind"] = args.bls
@@ -491,7 +501,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    rows, my_ms, delta, info = window_job(bk, ctx, ls, n, u_front, s_total, rank, jw, torch, flush, nsteps=K * B)
+    spec = (dist, f"cuda:{dev}") if (world > 1 and args.partition == "speculative") else None
+    rows, my_ms, delta, info = window_job(bk, ctx, ls, n, u_front, s_total, rank, 1 if spec else jw, torch, flush, nsteps=K * B, spec=spec)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -518,7 +529,7 @@ def main():
 
     # ---- e2e: the same job through the plugin / C ABI with HOST buffers (pinned NumPy state; H2D/D2H inside every call)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and spec is None:
         nthr, limiter = best_blas_threads(n * n, cores)
         if limiter is not None:
             limiter(limits=nthr, user_api="blas")
@@ -610,6 +621,8 @@ def main():
                "mean_itlinear_per_step": float(np.mean(branch[1:, 3])) if nst > 1 else 0.0,
                "corrector_work": {"newton_its": int(wn), "linear_its": int(wl)}, "rejected_steps": int(sum(p["rejected"] for p in per_rank)) if per_rank else int(info["rejected"]),
                "parallelism": ("1 GPU" if world == 1 else
+                               (f"one branch on {world} GPUs with speculative step sizes (segments.continuation_speculative): rank r corrects with the r-times-halved "
+                                f"step, all_gather of 4 doubles + broadcast of the accepted point per step; {info.get('speculative')}") if spec else
                                (f"replicas only: {world} independent replicas of the job, one per GPU; replicated state; all_gather of rows only; "
                                 f"max |row difference| between replicas = {replica_dev:g}") if replicas else
                                (f"one window cut into {world} chunks of equal predicted cost; replicated scout inside the timed region "
